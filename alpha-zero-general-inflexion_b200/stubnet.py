@@ -1,0 +1,53 @@
+"""Deterministic policy/value stub used for bit-exact parity runs and for tree-only throughput runs.
+
+The parity contract (BASELINE.json north_star) is "visit counts bit-exact against the reference's MCTS
+when both use a fixed deterministic net stub".  A stub that is to give the SAME float32 numbers on the
+CPU (reference / oracle side) and on the GPU (kernel side) must avoid every operation whose rounding is
+implementation defined, so it uses only int64 arithmetic, an int->float32 conversion and one IEEE float32
+division -- all of which torch evaluates identically on both devices.
+
+``stub_policy_value(planes)`` takes the network input batch ``[B,4,7,7]`` (any real dtype; it is the
+reference's ``to_planes()`` stack, ``inflexion/InflexionGame.py:84-91``) and returns ``(pi f32[B,343],
+v f32[B])`` with the dtypes/shapes of ``NNetWrapper.predict`` (``inflexion/pytorch/NNet.py:94``).
+"""
+from __future__ import annotations
+
+import torch
+
+_MASK31 = (1 << 31) - 1
+_COEF = None
+
+
+def _coef(device):
+    global _COEF
+    if _COEF is None:
+        g = torch.Generator().manual_seed(20231018)
+        _COEF = torch.randint(1, 1 << 20, (196,), generator=g, dtype=torch.int64) | 1
+    return _COEF.to(device)
+
+
+def _mix(h):
+    h = (h ^ (h >> 15)) & _MASK31
+    h = (h * 0x2C1B3C6D) & _MASK31
+    h = (h ^ (h >> 12)) & _MASK31
+    h = (h * 0x297A2D39) & _MASK31
+    return (h ^ (h >> 15)) & _MASK31
+
+
+def stub_policy_value(planes: torch.Tensor, mode: str = "float"):
+    """mode "dyadic": integer priors in [1,256] (every partial sum exact in float32, any order);
+    mode "float": priors k/1000003 (inexact, so the float32 summation ORDER is observable)."""
+    x = planes.reshape(planes.shape[0], 196).to(torch.int64)
+    h = _mix((x * _coef(x.device)).sum(dim=1) & _MASK31)                  # [B]
+    a = torch.arange(343, device=x.device, dtype=torch.int64)
+    z = _mix((h[:, None] + a[None, :] * 0x9E3779B) & _MASK31)             # [B,343]
+    sharp = (z & 0xFF) + 1                                                # 1..256
+    if mode == "dyadic":
+        pi = sharp.to(torch.float32)
+    else:
+        # a few large priors make the trees several plies deep, like a trained net's would
+        peaked = torch.where((z >> 8) % 11 == 0, sharp * 64, sharp)
+        pi = peaked.to(torch.float32) / torch.tensor(1000003.0, dtype=torch.float32, device=x.device)
+    hv = _mix(h ^ 0x5BD1E995)
+    v = ((hv & 0xFFFF) - 32768).to(torch.float32) / 32768.0               # dyadic in [-1, 1)
+    return pi, v
