@@ -1,0 +1,127 @@
+// Common definitions for the inflexion_b200 CUDA library (sm_100a).
+//
+// The same sources also compile as plain C++ with -DIFX_HOSTSIM.  That build exists ONLY so the kernel
+// logic can be checked in a container without a GPU (tests/hostsim); it emulates each warp as 32
+// sequential lanes.  The product never loads it: the Python package loads libifx_b200.so (nvcc, sm_100a)
+// and fails loudly if it or a CUDA device is missing.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/ifx_b200.h"
+
+#ifdef IFX_HOSTSIM
+  #define IFX_HD static inline
+  #define IFX_D static inline
+  #define IFX_LANE0 true
+  #define IFX_FOR_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+  #define IFX_SYNCWARP() do {} while (0)
+  static inline int ifx_popc64(uint64_t x) { return __builtin_popcountll(x); }
+  static inline int ifx_popc32(uint32_t x) { return __builtin_popcount(x); }
+  static inline int ifx_ffs32(uint32_t x) { return __builtin_ffs((int)x); }
+  // host build is compiled with -ffp-contract=off, so these are single IEEE operations
+  static inline float ifx_fmul(float a, float b) { return a * b; }
+  static inline float ifx_fadd(float a, float b) { return a + b; }
+  static inline float ifx_fdiv(float a, float b) { return a / b; }
+  static inline double ifx_dmul(double a, double b) { return a * b; }
+  static inline double ifx_dadd(double a, double b) { return a + b; }
+  static inline double ifx_ddiv(double a, double b) { return a / b; }
+  static inline double ifx_dsqrt(double a) { return sqrt(a); }
+#else
+  #include <cuda_runtime.h>
+  #define IFX_HD __device__ __forceinline__
+  #define IFX_D __device__ __forceinline__
+  #define IFX_LANE0 ((threadIdx.x & 31u) == 0u)
+  #define IFX_FOR_LANES(lane) for (int lane = (int)(threadIdx.x & 31u), _ifx_once = 1; _ifx_once; _ifx_once = 0)
+  #define IFX_SYNCWARP() __syncwarp()
+  IFX_D int ifx_popc64(uint64_t x) { return __popcll(x); }
+  IFX_D int ifx_popc32(uint32_t x) { return __popc(x); }
+  IFX_D int ifx_ffs32(uint32_t x) { return __ffs((int)x); }
+  // explicit round-to-nearest intrinsics: never contracted into FMA (numpy does separate operations)
+  IFX_D float ifx_fmul(float a, float b) { return __fmul_rn(a, b); }
+  IFX_D float ifx_fadd(float a, float b) { return __fadd_rn(a, b); }
+  IFX_D float ifx_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+  IFX_D double ifx_dmul(double a, double b) { return __dmul_rn(a, b); }
+  IFX_D double ifx_dadd(double a, double b) { return __dadd_rn(a, b); }
+  IFX_D double ifx_ddiv(double a, double b) { return __ddiv_rn(a, b); }
+  IFX_D double ifx_dsqrt(double a) { return __dsqrt_rn(a); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Per-lane variables and warp collectives.  On the device a LaneVar is one register per thread; in
+// the host simulation it is an array of 32 and the collectives loop.
+// ---------------------------------------------------------------------------------------------
+template <class T> struct LaneVar {
+#ifdef IFX_HOSTSIM
+  T v[32];
+  T& operator[](int l) { return v[l]; }
+  const T& operator[](int l) const { return v[l]; }
+#else
+  T v;
+  IFX_D T& operator[](int) { return v; }
+  IFX_D const T& operator[](int) const { return v; }
+#endif
+};
+
+#ifdef IFX_HOSTSIM
+static inline uint32_t lanes_ballot(const LaneVar<int>& p) {
+  uint32_t m = 0;
+  for (int l = 0; l < 32; ++l) if (p[l]) m |= 1u << l;
+  return m;
+}
+static inline int lanes_sum_i32(const LaneVar<int>& x) {
+  int s = 0;
+  for (int l = 0; l < 32; ++l) s += x[l];
+  return s;
+}
+static inline int lanes_max_i32(const LaneVar<int>& x) {
+  int s = x[0];
+  for (int l = 1; l < 32; ++l) s = x[l] > s ? x[l] : s;
+  return s;
+}
+// x[l] <- x[l] + x[l ^ mask]   (simultaneous butterfly step; float add is commutative so both partners agree)
+static inline void lanes_bfly_fadd(LaneVar<float>& x, int mask) {
+  float t[32];
+  for (int l = 0; l < 32; ++l) t[l] = x[l] + x[l ^ mask];
+  for (int l = 0; l < 32; ++l) x[l] = t[l];
+}
+template <class T> static inline T lanes_bcast(const LaneVar<T>& x, int src) { return x[src]; }
+// maximum u; ties go to the LOWEST action index (sequential scan with strict '>' in MCTS.py:119-129)
+static inline void lanes_argmax(const LaneVar<float>& u, const LaneVar<int>& a, float* bu, int* ba) {
+  float best = u[0]; int arg = a[0];
+  for (int l = 1; l < 32; ++l)
+    if (u[l] > best || (u[l] == best && a[l] < arg)) { best = u[l]; arg = a[l]; }
+  *bu = best; *ba = arg;
+}
+#else
+IFX_D uint32_t lanes_ballot(const LaneVar<int>& p) { return __ballot_sync(0xffffffffu, p.v != 0); }
+IFX_D int lanes_sum_i32(const LaneVar<int>& x) { return __reduce_add_sync(0xffffffffu, x.v); }
+IFX_D int lanes_max_i32(const LaneVar<int>& x) { return __reduce_max_sync(0xffffffffu, x.v); }
+IFX_D void lanes_bfly_fadd(LaneVar<float>& x, int mask) {
+  x.v = __fadd_rn(x.v, __shfl_xor_sync(0xffffffffu, x.v, mask));
+}
+template <class T> IFX_D T lanes_bcast(const LaneVar<T>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
+IFX_D void lanes_argmax(const LaneVar<float>& u, const LaneVar<int>& a, float* bu, int* ba) {
+  float best = u.v; int arg = a.v;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    float ou = __shfl_xor_sync(0xffffffffu, best, off);
+    int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+    if (ou > best || (ou == best && oa < arg)) { best = ou; arg = oa; }
+  }
+  *bu = best; *ba = arg;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// constants of the game (inflexion/InflexionGame.py:14-21, 47-50, 68; main.py:34)
+// ---------------------------------------------------------------------------------------------
+#define IFX_N 7
+#define IFX_CELLS 49
+#define IFX_MOVES 7
+#define IFX_ACTIONS 343
+#define IFX_SPAWN 6
+#define IFX_MAX_POWER_AT_SPAWN 48
+#define IFX_BOARD_MASK ((1ull << 49) - 1ull)
+#define IFX_ROW 352            // padded action row (343 -> 352 floats = 11 x 128 B)

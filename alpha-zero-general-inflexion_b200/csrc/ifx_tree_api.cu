@@ -1,0 +1,315 @@
+// Tree kernels (one warp per game) and the ifx_mcts_* C ABI.  See include/ifx_b200.h for the contract.
+#include "ifx_tree.cuh"
+#include "ifx_host.cuh"
+#include <new>
+
+struct ifx_mcts {
+  ifx_mcts_config cfg;
+  ifx_mcts_layout lay;
+  TreeParams P;
+  void* workspace;
+};
+
+static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+static int check_cfg(const ifx_mcts_config* c) {
+  if (!c) return IFX_E_ARG;
+  if (c->n_games <= 0 || c->nodes_per_game < 32 || c->nodes_per_game > 16384) return IFX_E_ARG;
+  if (c->hash_per_game < 64 || (c->hash_per_game & (c->hash_per_game - 1))) return IFX_E_ARG;
+  if (c->hash_per_game < 2 * c->nodes_per_game) return IFX_E_ARG;
+  if (c->max_depth < 1 || c->max_depth > 512 || c->num_sims < 0) return IFX_E_ARG;
+  if (c->policy_is_logits != 0) return IFX_E_ARG;          // softmax is left to the net in this version
+  return IFX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-game bodies shared by the device kernels and the host simulation
+// ---------------------------------------------------------------------------------------------
+IFX_D void body_reset(const TreeParams& P, int g, const ifx_state* roots, const int32_t* which) {
+  if (which && !which[g]) return;
+  if (IFX_LANE0) P.roots[g] = roots[g];
+  IFX_SYNCWARP();
+  tree_begin_move(P, g, true);
+}
+
+IFX_D void body_set_roots(const TreeParams& P, int g, const ifx_state* roots) {
+  if (IFX_LANE0) P.roots[g] = roots[g];
+  IFX_SYNCWARP();
+  tree_begin_move(P, g, false);
+}
+
+IFX_D void body_advance(const TreeParams& P, int g, const int32_t* actions) {
+  ifx_state root = P.roots[g];
+  const int a = actions[g];
+  if (root.outcome == IFX_ONGOING) {
+    if (!ifx_action_valid(root, a)) {
+      if (IFX_LANE0) P.games[g].faults |= IFX_F_BADACTION;
+      IFX_SYNCWARP();
+      return;
+    }
+    ifx_apply(root, a);                                      // Coach.py:82
+    IFX_SYNCWARP();
+    if (IFX_LANE0) P.roots[g] = root;
+    IFX_SYNCWARP();
+  }
+  tree_begin_move(P, g, false);
+}
+
+IFX_D void body_root_stats(const TreeParams& P, int g, int32_t* counts, float* q32, double* q64, uint8_t* qkind,
+                           int32_t* ns) {
+  const int slot = tree_root_slot(P, g);
+  const uint32_t* nrow = slot >= 0 ? reinterpret_cast<const uint32_t*>(tree_row(P, g, slot, 1)) : nullptr;
+  const float* qrow = slot >= 0 ? tree_row(P, g, slot, 2) : nullptr;
+  const double* qd = slot >= 0 ? P.q64 + ((int64_t)g * P.C + slot) * 344 : nullptr;
+  IFX_FOR_LANES(l) {
+    for (int a = l; a < IFX_ACTIONS; a += 32) {
+      const uint32_t raw = nrow ? nrow[a] : 0u;
+      const uint32_t n = raw & ~IFX_N_TAG;
+      const bool is64 = (raw & IFX_N_TAG) != 0;
+      const int64_t o = (int64_t)g * IFX_ACTIONS + a;
+      if (counts) counts[o] = (int32_t)n;
+      if (q32) q32[o] = n ? qrow[a] : 0.0f;
+      if (q64) q64[o] = n ? (is64 ? qd[a] : (double)qrow[a]) : 0.0;
+      if (qkind) qkind[o] = (uint8_t)(n && !is64);
+    }
+  }
+  if (ns && IFX_LANE0) ns[g] = slot >= 0 ? P.node_ns[(int64_t)g * P.C + slot] : 0;
+}
+
+IFX_D void body_status(const TreeParams& P, int g, int32_t* status) {
+  if (!IFX_LANE0) return;
+  const IfxGame G = P.games[g];
+  int32_t* s = status + (int64_t)g * 8;
+  s[0] = G.sims_done; s[1] = G.pending; s[2] = G.faults; s[3] = G.move_idx;
+  s[4] = P.roots[g].outcome; s[5] = G.n_live; s[6] = G.free_top; s[7] = G.path_len;
+}
+
+#ifndef IFX_HOSTSIM
+#define TREE_WARPS 4
+#define TREE_BLOCK (TREE_WARPS * 32)
+
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_wave_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_stride, const float* __restrict__ nn_v,
+                 float* __restrict__ nn_in) {
+  __shared__ float buf[TREE_WARPS][IFX_ROW];
+  const int w = threadIdx.x >> 5, g = blockIdx.x * TREE_WARPS + w;
+  if (g < P.G) tree_wave_game(P, g, nn_pi, pi_stride, nn_v, nn_in, buf[w]);
+}
+
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_reset_kernel(TreeParams P, const ifx_state* __restrict__ roots, const int32_t* __restrict__ which) {
+  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < P.G) body_reset(P, g, roots, which);
+}
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_set_roots_kernel(TreeParams P, const ifx_state* __restrict__ roots) {
+  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < P.G) body_set_roots(P, g, roots);
+}
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_advance_kernel(TreeParams P, const int32_t* __restrict__ actions) {
+  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < P.G) body_advance(P, g, actions);
+}
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_root_stats_kernel(TreeParams P, int32_t* counts, float* q32, double* q64, uint8_t* qkind, int32_t* ns) {
+  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < P.G) body_root_stats(P, g, counts, q32, q64, qkind, ns);
+}
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_sample_kernel(TreeParams P, int temp_threshold, int32_t* __restrict__ actions) {
+  __shared__ int buf[TREE_WARPS][IFX_ROW];
+  const int w = threadIdx.x >> 5, g = blockIdx.x * TREE_WARPS + w;
+  if (g >= P.G) return;
+  const int a = tree_sample_action(P, g, temp_threshold, buf[w]);
+  if (IFX_LANE0) actions[g] = a;
+}
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_status_kernel(TreeParams P, int32_t* __restrict__ status) {
+  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < P.G) body_status(P, g, status);
+}
+__global__ void tree_get_roots_kernel(TreeParams P, uint4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)P.G * 4) out[i] = reinterpret_cast<const uint4*>(P.roots)[i];
+}
+__global__ void tree_counters_kernel(TreeParams P, unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long acc[4];
+  if (threadIdx.x < 4) acc[threadIdx.x] = 0ull;
+  __syncthreads();
+  unsigned long long v = 0, e = 0, t = 0, s = 0;
+  for (int g = threadIdx.x; g < P.G; g += blockDim.x) {
+    const IfxGame G = P.games[g];
+    v += G.n_visits; e += G.n_expand; t += G.n_term; s += G.n_sims;
+  }
+  atomicAdd(&acc[0], v); atomicAdd(&acc[1], e); atomicAdd(&acc[2], t); atomicAdd(&acc[3], s);
+  __syncthreads();
+  if (threadIdx.x < 4) out[threadIdx.x] = acc[threadIdx.x];
+}
+#define TREE_GRID(P) ((unsigned)(((P).G + TREE_WARPS - 1) / TREE_WARPS))
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int ifx_mcts_get_layout(const ifx_mcts_config* c, ifx_mcts_layout* L) {
+  if (check_cfg(c) || !L) return IFX_E_ARG;
+  const int64_t G = c->n_games, C = c->nodes_per_game, H = c->hash_per_game;
+  int64_t off = 0;
+  L->rows = off;       off = align256(off + G * C * 3 * IFX_ROW * 4);
+  L->q64 = off;        off = align256(off + G * C * 344 * 8);
+  L->node_key = off;   off = align256(off + G * C * 16);
+  L->node_ns = off;    off = align256(off + G * C * 4);
+  L->hash = off;       off = align256(off + G * H * 16);
+  L->free_stack = off; off = align256(off + G * C * 2);
+  L->per_game = off;   off = align256(off + G * (int64_t)sizeof(IfxGame));
+  L->path = off;       off = align256(off + G * c->max_depth * 4);
+  L->roots = off;      off = align256(off + G * (int64_t)sizeof(ifx_state));
+  L->leaves = off;     off = align256(off + G * (int64_t)sizeof(ifx_state));
+  L->total = off;
+  return IFX_OK;
+}
+
+size_t ifx_mcts_workspace_bytes(const ifx_mcts_config* c) {
+  ifx_mcts_layout L;
+  return ifx_mcts_get_layout(c, &L) ? 0 : (size_t)L.total;
+}
+
+int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts** out) {
+  ifx_mcts_layout L;
+  if (!out || !ws || ifx_mcts_get_layout(c, &L)) return IFX_E_ARG;
+  if (bytes < (size_t)L.total || ((uintptr_t)ws & 255)) return IFX_E_ARG;
+  ifx_mcts* m = new (std::nothrow) ifx_mcts;
+  if (!m) return IFX_E_ARG;
+  m->cfg = *c; m->lay = L; m->workspace = ws;
+  char* b = (char*)ws;
+  TreeParams& P = m->P;
+  P.rows = (float*)(b + L.rows); P.q64 = (double*)(b + L.q64); P.node_key = (IfxKey*)(b + L.node_key);
+  P.node_ns = (int32_t*)(b + L.node_ns); P.hash = (IfxKey*)(b + L.hash);
+  P.free_stack = (uint16_t*)(b + L.free_stack); P.games = (IfxGame*)(b + L.per_game);
+  P.path = (uint32_t*)(b + L.path); P.roots = (ifx_state*)(b + L.roots); P.leaves = (ifx_state*)(b + L.leaves);
+  P.G = c->n_games; P.C = c->nodes_per_game; P.H = c->hash_per_game; P.maxd = c->max_depth;
+  P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.cpuct = c->cpuct; P.seed = c->seed;
+  *out = m;
+  return IFX_OK;
+}
+
+void ifx_mcts_destroy(ifx_mcts* m) { delete m; }
+
+int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct) {
+  if (!m || num_sims < 0) return IFX_E_ARG;
+  m->P.num_sims = m->cfg.num_sims = num_sims;
+  m->P.cpuct = m->cfg.cpuct = cpuct;
+  return IFX_OK;
+}
+
+int ifx_mcts_reset_games(ifx_mcts* m, const ifx_state* roots, const int32_t* which, void* stream) {
+  if (!m || !roots) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  for (int g = 0; g < m->P.G; ++g) body_reset(m->P, g, roots, which);
+  return ifx_after_launch();
+#else
+  tree_reset_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, roots, which);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_set_roots(ifx_mcts* m, const ifx_state* roots, void* stream) {
+  if (!m || !roots) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  for (int g = 0; g < m->P.G; ++g) body_set_roots(m->P, g, roots);
+  return ifx_after_launch();
+#else
+  tree_set_roots_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, roots);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const float* nn_v, float* nn_in, void* stream) {
+  if (!m || !nn_pi || !nn_v || !nn_in || pi_stride < IFX_ACTIONS) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  float buf[IFX_ROW];
+  for (int g = 0; g < m->P.G; ++g) tree_wave_game(m->P, g, nn_pi, pi_stride, nn_v, nn_in, buf);
+  return ifx_after_launch();
+#else
+  tree_wave_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_root_stats(ifx_mcts* m, int32_t* counts, float* q32, double* q64, uint8_t* qkind, int32_t* ns,
+                        void* stream) {
+  if (!m) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  for (int g = 0; g < m->P.G; ++g) body_root_stats(m->P, g, counts, q32, q64, qkind, ns);
+  return ifx_after_launch();
+#else
+  tree_root_stats_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, counts, q32, q64, qkind, ns);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_sample_actions(ifx_mcts* m, int32_t temp_threshold, int32_t* actions, void* stream) {
+  if (!m || !actions) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  int buf[IFX_ROW];
+  for (int g = 0; g < m->P.G; ++g) actions[g] = tree_sample_action(m->P, g, temp_threshold, buf);
+  return ifx_after_launch();
+#else
+  tree_sample_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, temp_threshold, actions);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_advance(ifx_mcts* m, const int32_t* actions, void* stream) {
+  if (!m || !actions) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  for (int g = 0; g < m->P.G; ++g) body_advance(m->P, g, actions);
+  return ifx_after_launch();
+#else
+  tree_advance_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, actions);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_status(ifx_mcts* m, int32_t* status, void* stream) {
+  if (!m || !status) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  for (int g = 0; g < m->P.G; ++g) body_status(m->P, g, status);
+  return ifx_after_launch();
+#else
+  tree_status_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, status);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_get_roots(ifx_mcts* m, ifx_state* roots, void* stream) {
+  if (!m || !roots) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  memcpy(roots, m->P.roots, (size_t)m->P.G * sizeof(ifx_state));
+  return ifx_after_launch();
+#else
+  const int64_t n = (int64_t)m->P.G * 4;
+  tree_get_roots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m->P, reinterpret_cast<uint4*>(roots));
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_counters(ifx_mcts* m, uint64_t* counters, void* stream) {
+  if (!m || !counters) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  counters[0] = counters[1] = counters[2] = counters[3] = 0;
+  for (int g = 0; g < m->P.G; ++g) {
+    const IfxGame& G = m->P.games[g];
+    counters[0] += G.n_visits; counters[1] += G.n_expand; counters[2] += G.n_term; counters[3] += G.n_sims;
+  }
+  return ifx_after_launch();
+#else
+  tree_counters_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(m->P, reinterpret_cast<unsigned long long*>(counters));
+  return ifx_after_launch();
+#endif
+}
+
+}  // extern "C"

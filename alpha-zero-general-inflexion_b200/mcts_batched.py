@@ -1,0 +1,173 @@
+"""Batched MCTS over G concurrent game trees on one GPU (one warp per tree).
+
+Host-side driver of the ifx_mcts_* kernels (include/ifx_b200.h).  One instance replaces G instances of the
+reference's ``MCTS`` (MCTS.py:15-148) together with the per-move part of ``Coach.executeEpisode``
+(Coach.py:66-82): ``search`` = the ``numMCTSSims`` loop of ``getActionProb`` (MCTS.py:45-46) for all games in
+lock step, ``root_stats`` = the visit counts of MCTS.py:48-49, ``sample_actions`` = MCTS.py:51-60 + Coach.py:81,
+``advance`` = Coach.py:82.
+
+The policy/value net is a callable ``evaluate(nn_in f32 [G,4,7,7]) -> (pi f32 [G,343], v f32 [G])`` working
+on device tensors; per move it is called at most ``num_sims`` times with the full batch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from .backend import Backend, default_backend
+
+
+def default_pool_size(num_sims: int) -> int:
+    """Nodes per game.  Live nodes (turn > root turn) were measured at <= 2.8 x sims; the bound
+    is depth x sims, so keep a wide margin and fail loudly (IFX_F_POOL) rather than silently."""
+    n = 64
+    while n < 10 * max(num_sims, 1):
+        n *= 2
+    return min(n, 16384)
+
+
+class BatchedMCTS:
+    def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | None = None,
+                 max_depth: int = 64, backend: Backend | None = None):
+        self.be = backend or default_backend()
+        self.n_games, self.num_sims = int(n_games), int(num_sims)
+        nodes = int(nodes_per_game or default_pool_size(num_sims))
+        hash_slots = 64
+        while hash_slots < 2 * nodes:
+            hash_slots *= 2
+        # float32(cpuct): the reference multiplies a Python number into a float32 (NEP-50 weak scalar, MCTS.py:122)
+        self.cfg = _capi.MctsConfig(n_games=self.n_games, nodes_per_game=nodes, hash_per_game=hash_slots,
+                                    max_depth=max_depth, num_sims=self.num_sims, cpuct=float(np.float32(cpuct)),
+                                    seed=int(seed) & (2 ** 64 - 1), policy_is_logits=0, reserved=0)
+        dll = self.be.dll
+        self.layout = _capi.MctsLayout()
+        self.be.check(dll.ifx_mcts_get_layout(C.byref(self.cfg), C.byref(self.layout)))
+        nbytes = dll.ifx_mcts_workspace_bytes(C.byref(self.cfg))
+        # the caller owns the workspace: one uint8 tensor (+256 B so the base can be aligned)
+        self._ws_raw = self.be.empty((nbytes + 256,), torch.uint8)
+        off = (-self._ws_raw.data_ptr()) % 256
+        self.workspace = self._ws_raw[off:off + nbytes]
+        handle = C.c_void_p()
+        self.be.check(dll.ifx_mcts_create(C.byref(self.cfg), self.workspace.data_ptr(), nbytes, C.byref(handle)))
+        self._h = handle
+        g = self.n_games
+        # net I/O buffers (persistent so the wave + net step can be captured in a CUDA graph)
+        self.nn_in = self.be.zeros((g, 4, 7, 7), torch.float32)
+        self.nn_pi = self.be.zeros((g, 343), torch.float32)
+        self.nn_v = self.be.zeros((g,), torch.float32)
+        self.waves_run = 0
+        self.evals_run = 0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self.be.dll.ifx_mcts_destroy(h)
+            except Exception:
+                pass
+
+    # ---- tree lifecycle -------------------------------------------------------------------------
+    def reset(self, roots, which: torch.Tensor | None = None) -> None:
+        """Empty the trees (of the games selected by ``which``) and install ``roots``; roots[g].tag = game id."""
+        r = self.be.states_tensor(roots)
+        assert r.shape == (self.n_games, 64)
+        w = None if which is None else which.to(self.be.device, torch.int32).contiguous()
+        self.be.check(self.be.dll.ifx_mcts_reset_games(self._h, r.data_ptr(), None if w is None else w.data_ptr(),
+                                                       self.be.stream()))
+        self._keep = (r, w)
+
+    def set_roots(self, roots) -> None:
+        """Next getActionProb on new root states, keeping the tables (the reference never clears them)."""
+        r = self.be.states_tensor(roots)
+        assert r.shape == (self.n_games, 64)
+        self.be.check(self.be.dll.ifx_mcts_set_roots(self._h, r.data_ptr(), self.be.stream()))
+        self._keep = (r, None)
+
+    def set_params(self, num_sims: int, cpuct) -> None:
+        self.num_sims = int(num_sims)
+        self.be.check(self.be.dll.ifx_mcts_set_params(self._h, self.num_sims, float(np.float32(cpuct))))
+
+    # ---- search ---------------------------------------------------------------------------------
+    def wave(self) -> None:
+        self.be.check(self.be.dll.ifx_mcts_wave(self._h, self.nn_pi.data_ptr(), self.nn_pi.stride(0),
+                                                self.nn_v.data_ptr(), self.nn_in.data_ptr(), self.be.stream()))
+        self.waves_run += 1
+
+    def search(self, evaluate) -> None:
+        """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync."""
+        for _ in range(self.num_sims):
+            self.wave()
+            pi, v = evaluate(self.nn_in)
+            if pi is not self.nn_pi:
+                self.nn_pi.copy_(pi)
+            if v is not self.nn_v:
+                self.nn_v.copy_(v.reshape(-1))
+            self.evals_run += 1
+        self.wave()
+
+    # ---- results --------------------------------------------------------------------------------
+    def root_stats(self, want_q: bool = False) -> dict:
+        g = self.n_games
+        out = {"counts": self.be.empty((g, 343), torch.int32), "ns": self.be.empty((g,), torch.int32)}
+        if want_q:
+            out["q32"] = self.be.empty((g, 343), torch.float32)
+            out["q64"] = self.be.empty((g, 343), torch.float64)
+            out["qkind"] = self.be.empty((g, 343), torch.uint8)
+        p = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
+        self.be.check(self.be.dll.ifx_mcts_root_stats(self._h, p("counts"), p("q32"), p("q64"), p("qkind"), p("ns"),
+                                                      self.be.stream()))
+        return out
+
+    def sample_actions(self, temp_threshold: int) -> torch.Tensor:
+        a = self.be.empty((self.n_games,), torch.int32)
+        self.be.check(self.be.dll.ifx_mcts_sample_actions(self._h, int(temp_threshold), a.data_ptr(), self.be.stream()))
+        return a
+
+    def advance(self, actions: torch.Tensor) -> None:
+        assert actions.dtype == torch.int32 and actions.shape == (self.n_games,)
+        self.be.check(self.be.dll.ifx_mcts_advance(self._h, actions.data_ptr(), self.be.stream()))
+        self._keep_a = actions
+
+    def status(self) -> torch.Tensor:
+        """int32 [G,8]: sims_done, pending, fault bits, move index, root outcome, live nodes, free nodes, path length."""
+        s = self.be.empty((self.n_games, 8), torch.int32)
+        self.be.check(self.be.dll.ifx_mcts_status(self._h, s.data_ptr(), self.be.stream()))
+        return s
+
+    def raise_on_faults(self) -> None:
+        f = self.status()[:, 2]
+        if bool((f != 0).any()):
+            bad = torch.nonzero(f).flatten()[:8].tolist()
+            bits = int(f[bad[0]])
+            raise _capi.IfxError(f"MCTS fault in games {bad}: {_capi.fault_text(bits)}")
+
+    def roots(self) -> torch.Tensor:
+        r = self.be.empty((self.n_games, 64), torch.uint8)
+        self.be.check(self.be.dll.ifx_mcts_get_roots(self._h, r.data_ptr(), self.be.stream()))
+        return r
+
+    def counters(self) -> dict:
+        c = self.be.empty((4,), torch.int64)
+        self.be.check(self.be.dll.ifx_mcts_counters(self._h, c.data_ptr(), self.be.stream()))
+        v, e, t, s = c.tolist()
+        return {"node_visits": v, "expansions": e, "terminals": t, "sims": s}
+
+    # ---- inspection (tests) -----------------------------------------------------------------------
+    def table_views(self) -> dict:
+        """numpy views of the SoA pools (copies the workspace to the host)."""
+        ws = self.workspace.cpu().numpy()
+        L, c = self.layout, self.cfg
+        g, n, h = c.n_games, c.nodes_per_game, c.hash_per_game
+
+        def view(off, dtype, shape):
+            count = int(np.prod(shape))
+            return np.frombuffer(ws, dtype=dtype, count=count, offset=off).reshape(shape)
+        rows = view(L.rows, np.uint32, (g, n, 3, 352))
+        return {
+            "P": rows[:, :, 0, :343].view(np.float32), "Nraw": rows[:, :, 1, :343], "Q32": rows[:, :, 2, :343].view(np.float32),
+            "Q64": view(L.q64, np.float64, (g, n, 344))[:, :, :343],
+            "key": view(L.node_key, np.uint64, (g, n, 2)), "ns": view(L.node_ns, np.int32, (g, n)),
+        }

@@ -1,0 +1,191 @@
+/* ifx_b200.h -- C ABI of libifx_b200.so: the Inflexion rules engine and batched MCTS on sm_100a.
+ *
+ * The reference (Meatssauce/alpha-zero-general-inflexion) is pure Python and has NO FFI boundary for this
+ * path; the boundary is designed here and each entry point cites the Python interface it replaces
+ * (paths relative to the reference root).  The Python classes in alpha-zero-general-inflexion_b200/
+ * (InflexionGame, MCTS, ...) bind these symbols with ctypes and keep the reference's API surface.
+ *
+ * Conventions
+ *   - plain C, no torch types; pointers are DEVICE pointers unless the function name ends in _host;
+ *   - every device entry point is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default);
+ *   - return value: 0 = ok, negative = IFX_E_* (argument / launch error).  Per-game runtime faults
+ *     (pool exhausted, no valid action, ...) are reported through ifx_mcts_status, never by aborting;
+ *   - the caller owns every buffer (including the MCTS workspace); the library frees nothing it did not
+ *     allocate.  One ifx_mcts handle per GPU/process; a handle is not thread-safe.
+ */
+#ifndef IFX_B200_H
+#define IFX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFX_API __attribute__((visibility("default")))
+
+/* ---- error codes --------------------------------------------------------------------------- */
+#define IFX_OK 0
+#define IFX_E_ARG (-1)      /* bad argument (null pointer, size, alignment)                      */
+#define IFX_E_CUDA (-2)     /* CUDA runtime error; see ifx_last_cuda_error()                     */
+#define IFX_E_NODEVICE (-3) /* no CUDA device                                                    */
+
+/* ---- per-game fault bits (ifx_mcts_status column 2) ----------------------------------------- */
+#define IFX_F_POOL 1     /* node pool exhausted: raise nodes_per_game                            */
+#define IFX_F_NOVALID 2  /* side to move has no valid action (the reference crashes, MCTS.py:116,131) */
+#define IFX_F_DEPTH 4    /* search path deeper than max_depth                                    */
+#define IFX_F_HASH 8     /* hash table full                                                      */
+#define IFX_F_BADACTION 16 /* advance/step called with an action that is not valid               */
+
+/* ---- outcome codes, relative to the side to move (flags.py:32-44, Game.py:64-72) ------------- */
+#define IFX_ONGOING 0
+#define IFX_DRAW 1  /* value 1e-4 */
+#define IFX_WON 2   /* value +1   */
+#define IFX_LOST 3  /* value -1   */
+
+/* Packed game state, 64 bytes, 16-byte aligned.  Replaces the attributes of InflexionGame
+ * (inflexion/InflexionGame.py:57-69, Game.py:21-25): _board int64[7,7] in [-6,6] (sign = owner),
+ * _player, _curr_turn, _outcome, _max_turns.  Bit i = r*7+q of a mask is cell (r,q).
+ * Stack power of a cell = p0 + 2*p1 + 4*p2 (1..6); red/blue are the ownership masks. */
+typedef struct ifx_state {
+  uint64_t red, blue;      /* cells owned by RED (+) / BLUE (-)                                  */
+  uint64_t p0, p1, p2;     /* bit planes of |power|                                              */
+  uint16_t turn;           /* _curr_turn                                                         */
+  uint16_t max_turns;      /* _max_turns                                                         */
+  uint8_t player;          /* side to move: 0 = RED, 1 = BLUE                                    */
+  uint8_t outcome;         /* IFX_ONGOING/DRAW/WON/LOST w.r.t. the side to move                  */
+  uint8_t total_power;     /* sum |board| (cached; InflexionGame.py:347)                         */
+  uint8_t flags;           /* reserved                                                           */
+  uint32_t tag;            /* caller tag; for MCTS roots: the game id (RNG stream coordinate)    */
+  uint32_t reserved[3];
+} ifx_state;
+
+/* ---- library ------------------------------------------------------------------------------- */
+IFX_API int ifx_version(void);
+IFX_API const char* ifx_last_cuda_error(void);
+IFX_API int64_t ifx_launch_count(void); /* kernels launched by this library so far (bench evidence) */
+IFX_API int ifx_is_hostsim(void);       /* 1 only in the GPU-less logic-check build used by tests/   */
+
+/* ---- rules engine: one thread per state ------------------------------------------------------ */
+
+/* valid_actions_mask (InflexionGame.py:93-100) fused with to_next_state/execute_move
+ * (InflexionGame.py:75-82, 273-310).  masks[i][m] (m = 0..6) is the 49-bit cell mask of move type m for
+ * states_in[i] (bit r*7+q  <=>  action m*49+r*7+q is valid).  states_out[i] = states_in[i] after
+ * actions[i]; status[i] = 0, or IFX_F_BADACTION (state copied through unchanged) when the action is not
+ * valid, which is where the reference raises ValueError / asserts (InflexionGame.py:279,282,291).
+ * actions may be NULL (mask only) and masks may be NULL (step only). */
+IFX_API int ifx_rules_mask_step(const ifx_state* states_in, const int32_t* actions, int64_t n,
+                                uint64_t* masks /* [n][7] */, ifx_state* states_out, int32_t* status,
+                                void* stream);
+
+/* to_planes (InflexionGame.py:84-91) with an optional board symmetry applied
+ * (random_symmetry, InflexionGame.py:115-122): sym[i] = k + 6*shift + 42*axis, k = rotation 0..5,
+ * shift 0..6, axis 0..2 = 'r','q','s'; NULL = identity.  dtype: 0 = float32, 1 = int64. out is [n][4][7][7]. */
+IFX_API int ifx_rules_planes(const ifx_state* states, const int32_t* sym, int64_t n, int dtype, void* out,
+                             void* stream);
+
+/* symmetries (InflexionGame.py:102-113): the 36 isomorphic forms of each [channels][7][7] array of
+ * elem_size-byte elements (4 or 8), in the reference's order.  out is [n][36][channels][7][7]. */
+IFX_API int ifx_rules_symmetries(const void* in, int64_t n, int channels, int elem_size, void* out,
+                                 void* stream);
+
+/* score / piece_count_diff / power_diff / total_power (InflexionGame.py:198-199, 312-323, 347):
+ * info[i] = { score for side to move, power_diff for side to move, total_power, number of valid actions }. */
+IFX_API int ifx_rules_info(const ifx_state* states, int64_t n, int32_t* info /* [n][4] */, void* stream);
+
+/* Host-buffer forms of the above (plain host pointers; copies in, launches, copies out, synchronises).
+ * These are what the object-per-game drop-in API (InflexionGame.to_next_state etc.) calls. */
+IFX_API int ifx_rules_mask_step_host(const ifx_state* states_in, const int32_t* actions, int64_t n,
+                                     uint64_t* masks, ifx_state* states_out, int32_t* status);
+IFX_API int ifx_rules_planes_host(const ifx_state* states, const int32_t* sym, int64_t n, int dtype, void* out);
+IFX_API int ifx_rules_symmetries_host(const void* in, int64_t n, int channels, int elem_size, void* out);
+IFX_API int ifx_rules_info_host(const ifx_state* states, int64_t n, int32_t* info);
+
+/* ---- batched MCTS: one warp per game tree ----------------------------------------------------- */
+
+typedef struct ifx_mcts_config {
+  int32_t n_games;          /* concurrent game trees on this GPU                                  */
+  int32_t nodes_per_game;   /* node pool capacity per game (<= 16384)                             */
+  int32_t hash_per_game;    /* hash slots per game, power of two, >= 2*nodes_per_game             */
+  int32_t max_depth;        /* longest search path kept (<= 512)                                  */
+  int32_t num_sims;         /* args.numMCTSSims (MCTS.py:45)                                      */
+  float cpuct;              /* float32(args.cpuct) (MCTS.py:122; NEP-50 weak scalar)              */
+  uint64_t seed;            /* Philox key for every random draw on the path    */
+  int32_t policy_is_logits; /* 0: nn_pi holds probabilities (NNet.py:94 exp(log_softmax));
+                               1: nn_pi holds raw logits, softmax fused into the expansion        */
+  int32_t reserved;
+} ifx_mcts_config;
+
+typedef struct ifx_mcts ifx_mcts;
+
+/* Offsets (bytes) of the SoA pools inside the workspace, for inspection by tests (MCTS tables
+ * Qsa/Nsa/Ns/Ps of MCTS.py:25-31 are not read by any caller of the reference). */
+typedef struct ifx_mcts_layout {
+  int64_t rows;       /* float [G][C][3][352]: P, N (int32, bit31 = Q is a Python-float), Q (float32)  */
+  int64_t q64;        /* double [G][C][344]: Q when its kind is Python-float       */
+  int64_t node_key;   /* uint64 [G][C][2]                                                               */
+  int64_t node_ns;    /* int32 [G][C]                                                                   */
+  int64_t hash;       /* uint64 [G][H][2]                                                               */
+  int64_t free_stack; /* uint16 [G][C]                                                                  */
+  int64_t per_game;   /* struct per game, see csrc/ifx_tree.cuh                                         */
+  int64_t path;       /* uint32 [G][max_depth]                                                          */
+  int64_t roots;      /* ifx_state [G]                                                                  */
+  int64_t leaves;     /* ifx_state [G]                                                                  */
+  int64_t total;      /* == ifx_mcts_workspace_bytes                                                    */
+} ifx_mcts_layout;
+
+IFX_API int ifx_mcts_get_layout(const ifx_mcts_config* cfg, ifx_mcts_layout* out);
+IFX_API size_t ifx_mcts_workspace_bytes(const ifx_mcts_config* cfg);
+
+/* MCTS.__init__ (MCTS.py:21-31).  `workspace` is a device buffer of ifx_mcts_workspace_bytes, 256-B aligned. */
+IFX_API int ifx_mcts_create(const ifx_mcts_config* cfg, void* workspace, size_t workspace_bytes, ifx_mcts** out);
+IFX_API void ifx_mcts_destroy(ifx_mcts* m);
+IFX_API int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct);
+
+/* Empty trees + install roots (MCTS.reset, MCTS.py:147-148, followed by the first getActionProb).
+ * roots[g].tag is the game id used as the RNG stream coordinate.  `which` (nullable, int32 [G]) selects
+ * the games to reset; others are untouched. */
+IFX_API int ifx_mcts_reset_games(ifx_mcts* m, const ifx_state* roots, const int32_t* which, void* stream);
+
+/* Start the next getActionProb on new roots while keeping the trees (the reference never clears its
+ * tables between moves: Coach.py:110, InflexionPlayers.py:86-88).  Nodes whose turn plane makes them
+ * unreachable from the new root are reclaimed. */
+IFX_API int ifx_mcts_set_roots(ifx_mcts* m, const ifx_state* roots, void* stream);
+
+/* One lock-step wave over all games (MCTS.search, MCTS.py:62-145):
+ *   1. if the game has a pending leaf, expand it from nn_pi[g] / nn_v[g] (MCTS.py:89-112) and back the
+ *      value up its path (MCTS.py:134-145);
+ *   2. run further simulations -- PUCT descent (MCTS.py:114-132), terminal leaves backed up at once
+ *      (MCTS.py:85-87) -- until a simulation reaches an unexpanded state or num_sims are done;
+ *   3. the unexpanded state's planes, under the random symmetry of MCTS.py:91-92, are written to
+ *      nn_in[g] as float32 [4][7][7] and the game waits for the net.
+ * A move needs at most num_sims net evaluations, i.e. num_sims+1 calls of this function. */
+IFX_API int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const float* nn_v, float* nn_in,
+                          void* stream);
+
+/* Root tables after the search (getActionProb, MCTS.py:48-49): any output may be NULL.
+ * counts int32 [G][343]; q32 float [G][343]; q64 double [G][343]; qkind uint8 [G][343] (1 = float32 kind,
+ * 0 = Python-float kind); ns int32 [G]. */
+IFX_API int ifx_mcts_root_stats(ifx_mcts* m, int32_t* counts, float* q32, double* q64, uint8_t* qkind,
+                                int32_t* ns, void* stream);
+
+/* Action choice of Coach.executeEpisode (Coach.py:66-81 with MCTS.py:51-60): temp = (move+1 < temp_threshold);
+ * temp 0 = uniform among arg-max counts, temp 1 = inverse-CDF sample of counts/sum in float64.
+ * actions int32 [G] (-1 for games that are over). */
+IFX_API int ifx_mcts_sample_actions(ifx_mcts* m, int32_t temp_threshold, int32_t* actions, void* stream);
+
+/* game = game.to_next_state(action) for every game (Coach.py:82) and start the next move. */
+IFX_API int ifx_mcts_advance(ifx_mcts* m, const int32_t* actions, void* stream);
+
+/* status int32 [G][8]: sims_done, pending, fault bits, move index, root outcome, live nodes, free nodes, 0. */
+IFX_API int ifx_mcts_status(ifx_mcts* m, int32_t* status, void* stream);
+/* roots out: ifx_state [G] (current root of every game). */
+IFX_API int ifx_mcts_get_roots(ifx_mcts* m, ifx_state* roots, void* stream);
+/* counters uint64 [4]: node visits V (expanded nodes traversed), expansions E, terminal leaves, simulations. */
+IFX_API int ifx_mcts_counters(ifx_mcts* m, uint64_t* counters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFX_B200_H */

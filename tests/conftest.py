@@ -4,8 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
 
 import inflexion_b200  # noqa: E402,F401  registers the package alias
 
@@ -19,3 +20,20 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", params=["hostsim", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request):
+    """'cuda' = the product library on the GPU (the parity tests proper, -m gpu);
+    'hostsim' = the same kernel sources compiled for the CPU (logic check in the GPU-less container)."""
+    if request.param == "cuda":
+        from inflexion_b200.backend import Backend
+        return Backend.cuda()
+    from hostsim import hostsim_backend
+    return hostsim_backend()
+
+
+@pytest.fixture(scope="session")
+def cuda_backend():
+    from inflexion_b200.backend import Backend
+    return Backend.cuda()

@@ -1,0 +1,163 @@
+"""The tree kernels (through the C ABI) against the golden episodes frozen from the live reference and against
+the oracle: root visit counts, Q bit patterns and kinds, Ns, sampled actions -- all bit exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from inflexion_b200.mcts_batched import BatchedMCTS
+from inflexion_b200.state import STATE_DTYPE, pack_states, unpack_boards
+from inflexion_b200.stubnet import stub_policy_value
+from oracle.inflexion_mcts import OracleMCTS, PhiloxDraws, sample_action, self_play_moves
+from oracle.inflexion_rules import OracleGame
+
+EPISODES = ["a_float_25", "b_dyadic_50", "c_short_full", "d_short_full"]
+
+
+def start_states(n, max_turns, tags=None):
+    return pack_states(np.zeros((n, 49), dtype=np.int64), 1, 0, 0, max_turns,
+                       tags=np.arange(n) if tags is None else tags)
+
+
+def stub_eval(mode):
+    return lambda nn_in: stub_policy_value(nn_in, mode)
+
+
+def stub_predict(mode):
+    def predict(planes):
+        pi, v = stub_policy_value(torch.from_numpy(np.ascontiguousarray(planes))[None], mode)
+        return pi.numpy()[0], v.numpy()[0]
+    return predict
+
+
+@pytest.mark.parametrize("name", EPISODES)
+def test_golden_episode(backend, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
+    cpuct = int(g["cpuct"]) if bool(g["cpuct_is_int"]) else float(g["cpuct"])
+    mode, sims, thr = str(g["mode"]), int(g["sims"]), int(g["temp_threshold"])
+    m = BatchedMCTS(1, sims, cpuct, seed=int(g["seed"]), backend=backend)
+    m.reset(start_states(1, int(g["max_turns"])))
+    for i in range(len(g["action"])):
+        m.search(stub_eval(mode))
+        m.raise_on_faults()
+        st = m.root_stats(want_q=True)
+        counts = st["counts"].cpu().numpy()[0]
+        assert np.array_equal(counts, g["counts"][i]), f"visit counts differ at move {i}"
+        seen = counts > 0
+        assert np.array_equal(st["qkind"].cpu().numpy()[0][seen], g["q_is32"][i][seen])
+        assert st["q64"].cpu().numpy()[0][seen].tobytes() == g["q"][i][seen].tobytes(), f"Q bits differ at move {i}"
+        assert int(st["ns"][0]) == g["ns"][i]
+        root = m.roots().cpu().numpy().view(STATE_DTYPE).reshape(-1)[0]
+        assert np.array_equal(unpack_boards(np.array([root]))[0], g["board"][i]) and root["turn"] == g["turn"][i]
+        a = m.sample_actions(thr)
+        assert int(a[0]) == g["action"][i], f"sampled action differs at move {i}"
+        m.advance(a)
+    status = m.status().cpu().numpy()[0]
+    assert status[2] == 0
+    if "ex_v" in g.files:
+        assert status[4] != 0          # the episode ended exactly where the reference's did
+    assert m.counters()["expansions"] == int(g["net_calls"])
+
+
+def test_many_games_match_oracle(backend):
+    """G independent trees (different RNG streams, different max_turns) against one oracle run each."""
+    G, sims, cpuct, seed, moves = 6, 20, 1.5, 77, 7
+    max_turns = np.array([343, 343, 6, 4, 343, 5])
+    m = BatchedMCTS(G, sims, cpuct, seed=seed, backend=backend)
+    m.reset(start_states(G, max_turns, tags=np.arange(G) + 100))
+    oracles = [self_play_moves(stub_predict("float"), sims, cpuct, PhiloxDraws(seed, game=100 + i), temp_threshold=3,
+                               max_moves=moves, max_turns=int(max_turns[i])) for i in range(G)]
+    alive = [True] * G
+    for mv in range(moves):
+        m.search(stub_eval("float"))
+        m.raise_on_faults()
+        counts = m.root_stats()["counts"].cpu().numpy()
+        acts = m.sample_actions(3)
+        a_np = acts.cpu().numpy()
+        for i in range(G):
+            if not alive[i]:
+                assert a_np[i] == -1
+                continue
+            rec = next(oracles[i])
+            assert np.array_equal(counts[i], rec["counts"]), (mv, i)
+            assert a_np[i] == rec["action"], (mv, i)
+            if rec["game"].outcome != 0:
+                alive[i] = False
+        m.advance(acts)
+    assert not all(alive) and any(alive)
+
+
+def test_full_tables_match_oracle(backend):
+    """Every live node (not just the root): P rows, N, Q and Ns against the oracle's dictionaries."""
+    sims, cpuct, seed = 30, 1, 5
+    m = BatchedMCTS(1, sims, cpuct, seed=seed, backend=backend)
+    m.reset(start_states(1, 8))
+    draws = PhiloxDraws(seed)
+    game = OracleGame(max_turns=8)
+    orc = OracleMCTS(stub_predict("float"), sims, cpuct, draws)
+    for mv in range(7):
+        orc.move = mv
+        pi = orc.get_action_prob(game, temp=1)
+        m.search(stub_eval("float"))
+        tv = m.table_views()
+        keys = tv["key"][0]
+        used = np.nonzero(keys[:, 0] != np.uint64(2 ** 64 - 1))[0]
+        # oracle nodes still reachable (turn > root turn, or the root)
+        live = {k: v for k, v in orc.P.items()
+                if np.frombuffer(k, dtype=np.int64)[2 * 49] > game.turn or k == game.key()}
+        assert len(used) == len(live)
+        for slot in used:
+            k0, k1 = int(keys[slot, 0]), int(keys[slot, 1])
+            own = np.array([(k0 >> c) & 1 for c in range(49)], dtype=np.int64)
+            opp = np.array([(k1 >> c) & 1 for c in range(49)], dtype=np.int64)
+            planes = np.stack([own, opp, np.full(49, k0 >> 49), np.full(49, (k1 >> 49) & 1)]).astype(np.int64)
+            key = planes.reshape(4, 7, 7).tobytes()
+            assert key in live
+            assert tv["P"][0, slot].tobytes() == orc.P[key].astype(np.float32).tobytes()
+            assert tv["ns"][0, slot] == orc.Ns[key]
+            for a in range(343):
+                n = int(tv["Nraw"][0, slot, a]) & 0x7FFFFFFF
+                assert n == orc.N.get((key, a), 0)
+                if n:
+                    q = orc.Q[(key, a)]
+                    is64 = bool(int(tv["Nraw"][0, slot, a]) >> 31)
+                    assert is64 == (not q.is32)
+                    got = tv["Q64"][0, slot, a] if is64 else np.float64(tv["Q32"][0, slot, a])
+                    assert np.float64(got).tobytes() == np.float64(q.x).tobytes()
+        a = sample_action(pi, draws.uniform(mv))
+        acts = m.sample_actions(1000)
+        assert int(acts[0]) == a
+        m.advance(acts)
+        game = game.to_next_state(a)
+        if game.outcome != 0:
+            break
+
+
+def test_uniform_fallback_when_all_valid_priors_are_zero(backend):
+    """MCTS.py:98-107: a policy that is zero on every valid move -> uniform over the valid moves."""
+    m = BatchedMCTS(2, 5, 1.0, seed=1, backend=backend)
+    m.reset(start_states(2, 343))
+
+    def zero_eval(nn_in):
+        return torch.zeros(2, 343, device=nn_in.device), torch.full((2,), 0.25, device=nn_in.device)
+    m.search(zero_eval)
+    m.raise_on_faults()
+    tv = m.table_views()
+    counts = m.root_stats()["counts"].cpu().numpy()
+    # root prior: 49 spawn actions, each 1/49 in float32; first sim expands the root, the other 4 visit children
+    assert counts.sum(axis=1).tolist() == [4, 4]
+    used = np.nonzero(tv["key"][0][:, 0] != np.uint64(2 ** 64 - 1))[0]
+    roots = [s for s in used if (int(tv["key"][0][s, 0]) >> 49) == 0]
+    p = tv["P"][0, roots[0]]
+    assert np.all(p[294:] == np.float32(1.0) / np.float32(49.0)) and np.all(p[:294] == 0)
+    # unseen edges tie at u = cpuct * P * sqrt(Ns + 1e-8): lowest index wins until visited
+    assert counts[0][294:298].tolist() == [1, 1, 1, 1]
+
+
+def test_pool_exhaustion_is_reported(backend):
+    m = BatchedMCTS(1, 40, 1.0, seed=1, nodes_per_game=32, backend=backend)
+    m.reset(start_states(1, 343))
+    m.search(stub_eval("float"))
+    with pytest.raises(Exception, match="pool"):
+        m.raise_on_faults()
