@@ -1,0 +1,105 @@
+"""``MCTS``: the reference's search object API (MCTS.py:15-148) over the CUDA tree kernel.
+
+    mcts = MCTS(nnet, args)              # args.numMCTSSims, args.cpuct
+    pi = mcts.getActionProb(game, temp)  # float64[343] (int8 one-hot at temp == 0)
+
+One object owns one device tree (a ``BatchedMCTS`` with a single game); ``getActionProb`` runs the
+``numMCTSSims`` simulations as kernel waves, keeps the tables between calls exactly as the reference does
+(Coach.py:110 builds one MCTS per episode) and reads the root visit counts back.  The net is called through
+``nnet.predict_batch`` (device tensors) when it has one, else through the reference-style
+``nnet.predict(planes)`` once per leaf.
+
+Random draws (leaf symmetry, MCTS.py:92; arg-max tie break, MCTS.py:53) come from the device's counter-based
+Philox stream, keyed by a seed taken from numpy's global RNG at construction -- so ``np.random.seed`` still
+makes a run reproducible, but the draws are not numpy's MT19937 stream.  For thousands of
+concurrent games use ``BatchedMCTS`` / ``SelfPlayEngine`` directly.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from .Game import Game
+from .mcts_batched import BatchedMCTS
+
+EPS = 1e-8
+log = logging.getLogger(__name__)
+
+
+class MCTS:
+    def __init__(self, nnet, args, seed: int | None = None, backend=None):
+        if not hasattr(nnet, "predict"):
+            raise TypeError("nnet must provide predict(planes) (NeuralNet.py:27-38)")
+        self.nnet = nnet
+        self.args = args
+        self._backend = backend
+        self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._tree: BatchedMCTS | None = None
+        self._last_turn = -1
+
+    # ---- net adapter ----------------------------------------------------------------------------------
+    def _evaluate(self, nn_in: torch.Tensor):
+        if hasattr(self.nnet, "predict_batch") and getattr(self.nnet, "device", nn_in.device) == nn_in.device:
+            return self.nnet.predict_batch(nn_in)
+        planes = nn_in[0].cpu().numpy().astype(np.int64)                  # what the reference hands to predict
+        pi, v = self.nnet.predict(planes)
+        pi = torch.as_tensor(np.asarray(pi, dtype=np.float32)).reshape(1, -1).to(nn_in.device)
+        v = torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(1).to(nn_in.device)
+        return pi, v
+
+    def _install_root(self, game) -> None:
+        sims, cpuct = int(self.args.numMCTSSims), self.args.cpuct
+        state = game._state.copy()
+        state["tag"] = 0
+        if self._tree is None:
+            self._tree = BatchedMCTS(1, sims, cpuct, seed=self._seed, backend=self._backend,
+                                     nodes_per_game=max(4096, 16 * sims) if sims <= 1024 else 16384)
+            self._tree.reset(state)
+        else:
+            self._tree.set_params(sims, cpuct)
+            if game._curr_turn < self._last_turn:
+                # nodes at or below the previous root's turn were reclaimed; the reference would still hold them
+                log.warning("MCTS: root turn moved backwards (%d -> %d); reusing a pruned tree",
+                            self._last_turn, game._curr_turn)
+            self._tree.set_roots(state)
+        self._last_turn = game._curr_turn
+
+    # ---- MCTS.py:33-60 ----------------------------------------------------------------------------------
+    def getActionProb(self, game, temp=1) -> np.ndarray:
+        if not isinstance(game, Game):
+            raise TypeError("game must be a Game")
+        if not (isinstance(temp, (int, float)) and temp >= 0):
+            raise ValueError("temp must be a non-negative number")
+        self._install_root(game)
+        self._tree.search_adaptive(self._evaluate)
+        self._tree.raise_on_faults()
+        counts = self._tree.root_stats()["counts"][0].cpu().numpy().astype(np.int64)
+        if temp == 0:
+            best = int(self._tree.sample_actions(0)[0])                   # uniform among the arg-max ties, on device
+            probs = np.zeros(len(counts), dtype=np.int8)
+            probs[best] = 1
+            return probs
+        counts = counts ** (1.0 / temp)
+        return counts / counts.sum()
+
+    def search(self, game):
+        """One simulation from ``game`` (MCTS.py:62-145).  Callers of the reference only reach this through
+        ``getActionProb``; provided for scripts that step the search by hand.  Returns None."""
+        saved = self.args.numMCTSSims
+        try:
+            self.args["numMCTSSims"] = 1
+            self._install_root(game)
+            self._tree.search_adaptive(self._evaluate)
+            self._tree.raise_on_faults()
+        finally:
+            self.args["numMCTSSims"] = saved
+
+    def reset(self):
+        return MCTS(self.nnet, self.args, backend=self._backend)          # MCTS.py:147-148
+
+    def dump(self) -> dict:
+        """Root tables of the last search (the reference's Qsa/Nsa/Ns for the root state)."""
+        out = self._tree.root_stats(want_q=True)
+        return {k: v[0].cpu().numpy() for k, v in out.items()}

@@ -36,10 +36,12 @@ PROTOTYPES = {
     "ifx_rules_mask_step": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ifx_rules_planes": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "ifx_rules_symmetries": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "ifx_rules_transform": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "ifx_rules_info": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ifx_rules_mask_step_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "ifx_rules_planes_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "ifx_rules_symmetries_host": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "ifx_rules_transform_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "ifx_rules_info_host": (c_int, [c_void_p, c_int64, c_void_p]),
     "ifx_mcts_get_layout": (c_int, [C.POINTER(MctsConfig), C.POINTER(MctsLayout)]),
     "ifx_mcts_workspace_bytes": (c_size_t, [C.POINTER(MctsConfig)]),

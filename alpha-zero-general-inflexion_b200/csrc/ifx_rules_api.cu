@@ -124,6 +124,17 @@ __global__ void rules_symmetries_kernel(const T* __restrict__ in, int64_t n, int
   out[e] = __ldg(in + (i * channels + c) * IFX_CELLS + ifx_sym_src(ifx_sym36(f), cell));
 }
 
+template <typename T>
+__global__ void rules_transform_kernel(const T* __restrict__ in, const int32_t* __restrict__ sym, int64_t n,
+                                       int channels, T* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)channels * IFX_CELLS;
+  if (e >= n * per) return;
+  const int64_t i = e / per;
+  const int rem = (int)(e - i * per), c = rem / IFX_CELLS, cell = rem - c * IFX_CELLS;
+  out[e] = __ldg(in + (i * channels + c) * IFX_CELLS + ifx_sym_src(__ldg(sym + i), cell));
+}
+
 __global__ void rules_info_kernel(const ifx_state* __restrict__ states, int64_t n, int32_t* __restrict__ info) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -209,6 +220,32 @@ int ifx_rules_symmetries(const void* in, int64_t n, int channels, int elem_size,
 #endif
 }
 
+int ifx_rules_transform(const void* in, const int32_t* sym, int64_t n, int channels, int elem_size, void* out,
+                        void* stream) {
+  if (n < 0 || channels <= 0 || (elem_size != 4 && elem_size != 8) || (n > 0 && (!in || !out || !sym))) return IFX_E_ARG;
+  if (n == 0) return IFX_OK;
+  const int64_t per = (int64_t)channels * IFX_CELLS;
+#ifdef IFX_HOSTSIM
+  for (int64_t e = 0; e < n * per; ++e) {
+    const int64_t i = e / per;
+    const int rem = (int)(e - i * per), c = rem / IFX_CELLS, cell = rem - c * IFX_CELLS;
+    if (sym[i] < 0 || sym[i] >= 126) return IFX_E_ARG;
+    const int64_t s = (i * channels + c) * IFX_CELLS + ifx_sym_src(sym[i], cell);
+    if (elem_size == 4) ((uint32_t*)out)[e] = ((const uint32_t*)in)[s];
+    else ((uint64_t*)out)[e] = ((const uint64_t*)in)[s];
+  }
+  return IFX_OK;
+#else
+  const unsigned blocks = (unsigned)((n * per + 255) / 256);
+  if (elem_size == 4)
+    rules_transform_kernel<uint32_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)in, sym, n, channels, (uint32_t*)out);
+  else
+    rules_transform_kernel<unsigned long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned long long*)in, sym, n, channels, (unsigned long long*)out);
+  return ifx_after_launch();
+#endif
+}
+
 int ifx_rules_info(const ifx_state* states, int64_t n, int32_t* info, void* stream) {
   if (n < 0 || (n > 0 && (!states || !info))) return IFX_E_ARG;
   if (n == 0) return IFX_OK;
@@ -272,6 +309,23 @@ int ifx_rules_symmetries_host(const void* in, int64_t n, int channels, int elem_
   int rc = ifx_rules_symmetries(d_in, n, channels, elem_size, d_out, nullptr);
   if (rc) return rc;
   if (ifx_d2h(out, d_out, ib * 36)) return IFX_E_CUDA;
+  return ifx_sync();
+}
+
+int ifx_rules_transform_host(const void* in, const int32_t* sym, int64_t n, int channels, int elem_size, void* out) {
+  if (n < 0 || channels <= 0 || (elem_size != 4 && elem_size != 8) || (n > 0 && (!in || !out || !sym))) return IFX_E_ARG;
+  if (n == 0) return IFX_OK;
+  for (int64_t i = 0; i < n; ++i) if (sym[i] < 0 || sym[i] >= 126) return IFX_E_ARG;
+  const size_t ib = (size_t)n * channels * IFX_CELLS * elem_size;
+  IfxScratch sc;
+  void* d_in = sc.take(ib);
+  void* d_out = sc.take(ib);
+  int32_t* d_sym = (int32_t*)sc.take(n * sizeof(int32_t));
+  if (!sc.ok()) return IFX_E_CUDA;
+  if (ifx_h2d(d_in, in, ib) || ifx_h2d(d_sym, sym, n * sizeof(int32_t))) return IFX_E_CUDA;
+  int rc = ifx_rules_transform(d_in, d_sym, n, channels, elem_size, d_out, nullptr);
+  if (rc) return rc;
+  if (ifx_d2h(out, d_out, ib)) return IFX_E_CUDA;
   return ifx_sync();
 }
 

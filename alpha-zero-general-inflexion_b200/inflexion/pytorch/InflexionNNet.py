@@ -1,0 +1,100 @@
+"""The policy/value CNN (reference architecture: inflexion/pytorch/InflexionNNet.py:11-54).
+
+Parameter names and shapes are those of the reference so its ``*.pth.tar`` checkpoints load unchanged:
+conv1..4 (3x3; the last two unpadded: 7->5->3) each with BatchNorm2d, fc1 4608->1024 and fc2 1024->512 with
+BatchNorm1d and dropout, heads fc3 512->343 (log-softmax) and fc4 512->1 (tanh).  12 526 424 parameters,
+404 287 488 FLOP per evaluation.
+
+``forward`` is the training-time graph.  Self-play does not call it: ``FoldedInference`` below is the
+inference form used by ``NNetWrapper.predict_batch`` -- BatchNorm folded into the preceding weights,
+channels-last bf16 activations on the tensor cores (cuDNN / cuBLAS; this is the only dense contraction on the
+path and stays in PyTorch by design), conv1 kept in fp32 because plane 2 carries the raw turn counter
+(0..343), which bf16 cannot represent above 256.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class InflexionNNet(nn.Module):
+    def __init__(self, game, args):
+        super().__init__()
+        self.depth, self.board_x, self.board_y = 4, *game.board_shape
+        self.action_size = game.max_actions
+        self.args = args
+        ch = args.num_channels
+        self.conv1 = nn.Conv2d(self.depth, ch, 3, stride=1, padding=1)
+        self.conv2 = nn.Conv2d(ch, ch, 3, stride=1, padding=1)
+        self.conv3 = nn.Conv2d(ch, ch, 3, stride=1)
+        self.conv4 = nn.Conv2d(ch, ch, 3, stride=1)
+        self.bn1, self.bn2, self.bn3, self.bn4 = (nn.BatchNorm2d(ch) for _ in range(4))
+        self.flat = ch * (self.board_x - 4) * (self.board_y - 4)
+        self.fc1 = nn.Linear(self.flat, 1024)
+        self.fc_bn1 = nn.BatchNorm1d(1024)
+        self.fc2 = nn.Linear(1024, 512)
+        self.fc_bn2 = nn.BatchNorm1d(512)
+        self.fc3 = nn.Linear(512, self.action_size)
+        self.fc4 = nn.Linear(512, 1)
+
+    def forward(self, s):
+        s = s.view(-1, self.depth, self.board_x, self.board_y)
+        for conv, bn in ((self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, self.bn3), (self.conv4, self.bn4)):
+            s = F.relu(bn(conv(s)))
+        s = s.reshape(-1, self.flat)
+        s = F.dropout(F.relu(self.fc_bn1(self.fc1(s))), p=self.args.dropout, training=self.training)
+        s = F.dropout(F.relu(self.fc_bn2(self.fc2(s))), p=self.args.dropout, training=self.training)
+        return F.log_softmax(self.fc3(s), dim=1), torch.tanh(self.fc4(s))
+
+
+def _fold(weight, bias, bn):
+    """y = bn(conv(x)) in eval mode == conv'(x) with w' = w * g/sqrt(var+eps), b' = (b - mean) * g/sqrt(var+eps) + beta."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    w = weight.detach().float() * scale.reshape(-1, *([1] * (weight.dim() - 1)))
+    b = (bias.detach().float() - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w, b
+
+
+class FoldedInference:
+    """Eval-mode forward of an ``InflexionNNet`` with BN folded in; call with float32 [B,4,7,7] on the device."""
+
+    def __init__(self, net: InflexionNNet, dtype=torch.bfloat16):
+        self.dtype = dtype
+        dev = next(net.parameters()).device
+        w1, b1 = _fold(net.conv1.weight, net.conv1.bias, net.bn1)
+        self.w1 = w1.contiguous(memory_format=torch.channels_last)           # fp32: exact turn plane
+        self.b1 = b1
+        self.convs = []
+        for conv, bn, pad in ((net.conv2, net.bn2, 1), (net.conv3, net.bn3, 0), (net.conv4, net.bn4, 0)):
+            w, b = _fold(conv.weight, conv.bias, bn)
+            self.convs.append((w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype), pad))
+        # fc1 consumes the NCHW flatten (c*9 + h*3 + w); permute its columns to the NHWC flatten we produce
+        w, b = _fold(net.fc1.weight, net.fc1.bias, net.fc_bn1)
+        ch = net.conv4.out_channels
+        hw = net.flat // ch
+        side = int(round(hw ** 0.5))
+        w = w.view(-1, ch, side, side).permute(0, 2, 3, 1).reshape(-1, net.flat)
+        self.fc1 = (w.to(dtype).contiguous(), b.to(dtype))
+        w, b = _fold(net.fc2.weight, net.fc2.bias, net.fc_bn2)
+        self.fc2 = (w.to(dtype).contiguous(), b.to(dtype))
+        # both heads in one GEMM: rows 0..342 = fc3, row 343 = fc4 (padded to 344 outputs)
+        wh = torch.cat([net.fc3.weight.detach().float(), net.fc4.weight.detach().float()], dim=0)
+        bh = torch.cat([net.fc3.bias.detach().float(), net.fc4.bias.detach().float()], dim=0)
+        self.head = (wh.to(dtype).contiguous(), bh.to(dtype))
+        self.n_act = net.action_size
+        self.device = dev
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor):
+        x = x.contiguous(memory_format=torch.channels_last)
+        s = F.relu(F.conv2d(x, self.w1, self.b1, padding=1)).to(self.dtype)
+        for w, b, pad in self.convs:
+            s = F.relu(F.conv2d(s, w, b, padding=pad))
+        s = s.permute(0, 2, 3, 1).reshape(s.shape[0], -1)                    # NHWC flatten: a view for channels-last
+        s = F.relu(F.linear(s, *self.fc1))
+        s = F.relu(F.linear(s, *self.fc2))
+        out = F.linear(s, *self.head).float()
+        pi = torch.exp(F.log_softmax(out[:, :self.n_act], dim=1))            # NNet.py:94
+        v = torch.tanh(out[:, self.n_act])
+        return pi, v

@@ -1,0 +1,124 @@
+"""``NNetWrapper``: the reference's network wrapper API (inflexion/pytorch/NNet.py:27-120) -- ``train``,
+``predict``, ``save_checkpoint``, ``load_checkpoint`` with the same hyper-parameters, losses and file format --
+plus ``predict_batch`` for the batched MCTS and data-parallel training when ``torch.distributed`` is
+initialised (gradients all-reduced over NCCL/NVLink; nothing else is communicated).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from ...NeuralNet import NeuralNet
+from ...utils import AverageMeter, dotdict
+from .InflexionNNet import FoldedInference, InflexionNNet
+
+# hyper-parameters of the reference (NNet.py:17-24)
+args = dotdict({
+    "lr": 0.001,
+    "dropout": 0.3,
+    "epochs": 10,
+    "batch_size": 512,
+    "cuda": torch.cuda.is_available(),
+    "num_channels": 512,
+})
+
+
+class NNetWrapper(NeuralNet):
+    def __init__(self, game, device=None, infer_dtype=torch.bfloat16):
+        self.nnet = InflexionNNet(game, args)
+        self.depth, self.board_x, self.board_y = 4, *game.board_shape
+        self.action_size = game.max_actions
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if args.cuda else torch.device("cpu")
+        self.device = torch.device(device)
+        self.nnet.to(self.device)
+        self.infer_dtype = infer_dtype
+        self._folded = None            # FoldedInference, rebuilt after every weight change
+
+    # ---- training (NNet.py:36-76) -----------------------------------------------------------------
+    def train(self, examples, verbose=True):
+        """examples: list of (planes, pi, v).  Adam with default lr (the reference never passes args.lr,
+        NNet.py:40), ``epochs`` x ``len/batch`` steps, each batch drawn WITH replacement (NNet.py:52).
+        Under torch.distributed every rank draws its own batch and gradients are averaged (all-reduce)."""
+        dist = torch.distributed if torch.distributed.is_available() and torch.distributed.is_initialized() else None
+        world = dist.get_world_size() if dist else 1
+        optimizer = optim.Adam(self.nnet.parameters())
+        boards_all = torch.as_tensor(np.array([e[0] for e in examples]).astype(np.float32))
+        pis_all = torch.as_tensor(np.array([e[1] for e in examples], dtype=np.float32))
+        vs_all = torch.as_tensor(np.array([e[2] for e in examples], dtype=np.float32))
+        params = [p for p in self.nnet.parameters() if p.requires_grad]
+        history = []
+        for epoch in range(args.epochs):
+            if verbose:
+                print("EPOCH ::: " + str(epoch + 1))
+            self.nnet.train()
+            pi_losses, v_losses = AverageMeter(), AverageMeter()
+            for _ in range(int(len(examples) / args.batch_size)):
+                ids = torch.from_numpy(np.random.randint(len(examples), size=args.batch_size))
+                boards = boards_all[ids].to(self.device, non_blocking=True)
+                target_pis = pis_all[ids].to(self.device, non_blocking=True)
+                target_vs = vs_all[ids].to(self.device, non_blocking=True)
+                out_pi, out_v = self.nnet(boards)
+                l_pi = self.loss_pi(target_pis, out_pi)
+                l_v = self.loss_v(target_vs, out_v)
+                optimizer.zero_grad()
+                (l_pi + l_v).backward()
+                if dist and world > 1:
+                    flat = torch.cat([p.grad.reshape(-1) for p in params])
+                    dist.all_reduce(flat)
+                    flat /= world
+                    off = 0
+                    for p in params:
+                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                        off += p.numel()
+                optimizer.step()
+                pi_losses.update(l_pi.item(), boards.size(0))
+                v_losses.update(l_v.item(), boards.size(0))
+            history.append((pi_losses.avg, v_losses.avg))
+            if verbose:
+                print(f"  Loss_pi={pi_losses} Loss_v={v_losses}")
+        self._folded = None
+        return history
+
+    # ---- inference --------------------------------------------------------------------------------
+    def predict(self, board):
+        """Batch-1 forward in fp32, exactly the reference's call (NNet.py:78-94): returns
+        (float32[343], float32 ndarray of shape (1,))."""
+        x = torch.as_tensor(np.asarray(board).astype(np.float32)).to(self.device).view(1, self.depth, self.board_x, self.board_y)
+        self.nnet.eval()
+        with torch.no_grad():
+            log_pi, v = self.nnet(x)
+        return torch.exp(log_pi).cpu().numpy()[0], v.cpu().numpy()[0]
+
+    def predict_batch(self, planes: torch.Tensor):
+        """float32 [B,4,7,7] on the device -> (pi float32 [B,343], v float32 [B]).  BN-folded bf16 graph."""
+        if self._folded is None:
+            self.nnet.eval()
+            self._folded = FoldedInference(self.nnet, self.infer_dtype)
+        return self._folded(planes)
+
+    def weights_changed(self):
+        self._folded = None
+
+    # ---- losses (NNet.py:96-100) --------------------------------------------------------------------
+    def loss_pi(self, targets, outputs):
+        return -torch.sum(targets * outputs) / targets.size()[0]
+
+    def loss_v(self, targets, outputs):
+        return torch.sum((targets - outputs.view(-1)) ** 2) / targets.size()[0]
+
+    # ---- checkpoints: torch.save({'state_dict': ...}) (NNet.py:102-120) --------------------------------
+    def save_checkpoint(self, folder="checkpoint", filename="checkpoint.pth.tar"):
+        os.makedirs(folder, exist_ok=True)
+        torch.save({"state_dict": self.nnet.state_dict()}, os.path.join(folder, filename))
+
+    def load_checkpoint(self, folder="checkpoint", filename="checkpoint.pth.tar"):
+        filepath = os.path.join(folder, filename)
+        if not os.path.exists(filepath):
+            raise FileNotFoundError(f"No model in path {filepath}")
+        checkpoint = torch.load(filepath, map_location=self.device)
+        self.nnet.load_state_dict(checkpoint["state_dict"])
+        self._folded = None

@@ -108,6 +108,21 @@ class BatchedMCTS:
             self.evals_run += 1
         self.wave()
 
+    def search_adaptive(self, evaluate) -> None:
+        """Same result as ``search`` but asks the device after every wave whether any game still waits for the
+        net (one small read-back per wave) and stops as soon as none does: the net is called exactly as often
+        as the reference calls ``predict``.  Used by the object-per-game drop-in, where a call is expensive."""
+        while True:
+            self.wave()
+            if not bool(self.status()[:, 1].any()):
+                return
+            pi, v = evaluate(self.nn_in)
+            if pi is not self.nn_pi:
+                self.nn_pi.copy_(pi)
+            if v is not self.nn_v:
+                self.nn_v.copy_(v.reshape(-1))
+            self.evals_run += 1
+
     # ---- results --------------------------------------------------------------------------------
     def root_stats(self, want_q: bool = False) -> dict:
         g = self.n_games

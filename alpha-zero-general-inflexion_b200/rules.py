@@ -56,6 +56,16 @@ def symmetries(x: torch.Tensor, backend: Backend | None = None) -> torch.Tensor:
     return out
 
 
+def transform(x: torch.Tensor, sym: torch.Tensor, backend: Backend | None = None) -> torch.Tensor:
+    """[S,C,7,7] -> translate(rotate(x, k), shift, axis) per item, sym int32 [S] = k + 6*shift + 42*axis."""
+    be = backend or default_backend()
+    assert x.dim() == 4 and x.shape[2:] == (7, 7) and x.is_contiguous() and x.element_size() in (4, 8)
+    out = torch.empty_like(x)
+    be.check(be.dll.ifx_rules_transform(_ptr(x), _ptr(sym), x.shape[0], x.shape[1], x.element_size(), _ptr(out),
+                                        be.stream()))
+    return out
+
+
 def info(states: torch.Tensor, backend: Backend | None = None) -> torch.Tensor:
     """-> int32 [S,4]: score, power_diff (side to move), total_power, number of valid actions."""
     be = backend or default_backend()
@@ -103,6 +113,17 @@ def symmetries_host(x: np.ndarray, backend=None) -> np.ndarray:
     assert x.ndim == 4 and x.shape[2:] == (7, 7) and x.itemsize in (4, 8)
     out = np.empty((x.shape[0], 36) + x.shape[1:], dtype=x.dtype)
     be.check(be.dll.ifx_rules_symmetries_host(_np_ptr(x), x.shape[0], x.shape[1], x.itemsize, _np_ptr(out)))
+    return out
+
+
+def transform_host(x: np.ndarray, sym, backend=None) -> np.ndarray:
+    be = backend or default_backend()
+    x = np.ascontiguousarray(x)
+    assert x.ndim == 4 and x.shape[2:] == (7, 7) and x.itemsize in (4, 8)
+    sym = np.ascontiguousarray(sym, dtype=np.int32).reshape(-1)
+    assert len(sym) == x.shape[0]
+    out = np.empty_like(x)
+    be.check(be.dll.ifx_rules_transform_host(_np_ptr(x), _np_ptr(sym), x.shape[0], x.shape[1], x.itemsize, _np_ptr(out)))
     return out
 
 

@@ -1,0 +1,221 @@
+"""Device-resident self-play for G concurrent Inflexion games on one GPU.
+
+``SelfPlayEngine`` is the batched form of ``Coach.executeEpisode`` (Coach.py:41-90): per move it runs the
+``numMCTSSims`` simulations of every game (tree kernel waves interleaved with batched net forwards), records
+the training example of the move (root state + visit counts + side to move), samples the action
+(temperature rule of Coach.py:66-68,81) and advances every game -- all on the device, no host round trip
+inside a move.  Examples are expanded to their 36 symmetric forms and given their value targets at the end
+(``examples()``), reproducing Coach.py:74-90 including the reference's player-alignment quirk
+unless ``fix_alignment=True``.
+
+Games are independent, so multi-GPU self-play is one engine per rank on its own shard of game ids with no
+communication.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import rules
+from .backend import Backend, default_backend
+from .mcts_batched import BatchedMCTS
+from .state import STATE_DTYPE, pack_states
+
+
+class SelfPlayEngine:
+    def __init__(self, n_games: int, num_sims: int, evaluate, cpuct=1.0, temp_threshold: int = 30, seed: int = 0,
+                 max_turns: int = 343, game_id_base: int = 0, nodes_per_game: int | None = None,
+                 record: bool = True, use_graph: bool | None = None, backend: Backend | None = None):
+        """evaluate(nn_in f32 [G,4,7,7]) -> (pi f32 [G,343], v f32 [G]) on the device (e.g. nnet.predict_batch)."""
+        self.be = backend or default_backend()
+        self.G, self.num_sims, self.temp_threshold = int(n_games), int(num_sims), int(temp_threshold)
+        self.max_turns, self.game_id_base = int(max_turns), int(game_id_base)
+        self.evaluate = evaluate
+        self.mcts = BatchedMCTS(self.G, num_sims, cpuct, seed=seed, nodes_per_game=nodes_per_game, backend=self.be)
+        self.record = record
+        self.max_moves = self.max_turns + 1                      # a game lasts at most max_turns+1 moves
+        if record:
+            self.ex_states = self.be.empty((self.max_moves, self.G, 64), torch.uint8)
+            self.ex_counts = self.be.empty((self.max_moves, self.G, 343), torch.int32)
+            self.ex_actions = self.be.empty((self.max_moves, self.G), torch.int32)
+        self.use_graph = self.be.is_cuda if use_graph is None else bool(use_graph)
+        self._graph = None
+        self.move = 0
+        self.my_launches = 0                                      # kernels of libifx_b200 launched (bench evidence)
+        self.restart()
+
+    # ---- episode control ----------------------------------------------------------------------------
+    def restart(self) -> None:
+        """game.restarted() + a fresh MCTS for every game (Coach.py:109-111)."""
+        roots = pack_states(np.zeros((self.G, 49), dtype=np.int64), 1, 0, 0, self.max_turns,
+                            tags=self.game_id_base + np.arange(self.G))
+        self.mcts.reset(roots)
+        self.move = 0
+        self.my_launches += 1
+
+    def _wave_and_net(self) -> None:
+        self.mcts.wave()
+        pi, v = self.evaluate(self.mcts.nn_in)
+        if pi is not self.mcts.nn_pi:
+            self.mcts.nn_pi.copy_(pi)
+        if v is not self.mcts.nn_v:
+            self.mcts.nn_v.copy_(v.reshape(-1))
+
+    def _capture(self) -> None:
+        """One (tree wave, net forward) pair as a CUDA graph; replayed num_sims times per move."""
+        s = torch.cuda.Stream(device=self.be.device)
+        s.wait_stream(torch.cuda.current_stream(self.be.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):                                   # warm the allocator / cuDNN heuristics on real data
+                pi, v = self.evaluate(self.mcts.nn_in)
+        torch.cuda.current_stream(self.be.device).wait_stream(s)
+        torch.cuda.synchronize(self.be.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._wave_and_net()
+
+    def search(self, wave_timer=None) -> None:
+        """The numMCTSSims loop for all games.  ``wave_timer(fn)`` (optional) wraps each tree-kernel launch, e.g.
+        to bracket it with CUDA events; it forces the un-captured path for the wave."""
+        if self.use_graph and wave_timer is None:
+            if self._graph is None:
+                self._capture()
+            for _ in range(self.num_sims):
+                self._graph.replay()
+            self.mcts.wave()
+        elif wave_timer is None:
+            for _ in range(self.num_sims):
+                self._wave_and_net()
+            self.mcts.wave()
+        else:
+            for _ in range(self.num_sims):
+                wave_timer(self.mcts.wave)
+                self._net_only()
+            wave_timer(self.mcts.wave)
+        self.my_launches += self.num_sims + 1
+
+    def _net_only(self) -> None:
+        if self.use_graph:
+            if getattr(self, "_net_graph", None) is None:
+                s = torch.cuda.Stream(device=self.be.device)
+                s.wait_stream(torch.cuda.current_stream(self.be.device))
+                with torch.cuda.stream(s):
+                    for _ in range(2):
+                        self.evaluate(self.mcts.nn_in)
+                torch.cuda.current_stream(self.be.device).wait_stream(s)
+                torch.cuda.synchronize(self.be.device)
+                self._net_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._net_graph):
+                    pi, v = self.evaluate(self.mcts.nn_in)
+                    self.mcts.nn_pi.copy_(pi)
+                    self.mcts.nn_v.copy_(v.reshape(-1))
+            self._net_graph.replay()
+        else:
+            pi, v = self.evaluate(self.mcts.nn_in)
+            self.mcts.nn_pi.copy_(pi)
+            self.mcts.nn_v.copy_(v.reshape(-1))
+
+    def finish_move(self) -> torch.Tensor:
+        """Record the example of this move, choose the action, play it.  Returns the actions (int32 [G], -1 = over)."""
+        m = self.mcts
+        if self.record and self.move < self.max_moves:
+            self.be.check(self.be.dll.ifx_mcts_get_roots(m._h, self.ex_states[self.move].data_ptr(), self.be.stream()))
+            self.be.check(self.be.dll.ifx_mcts_root_stats(m._h, self.ex_counts[self.move].data_ptr(), None, None, None,
+                                                          None, self.be.stream()))
+            acts = self.ex_actions[self.move]
+            self.be.check(self.be.dll.ifx_mcts_sample_actions(m._h, self.temp_threshold, acts.data_ptr(), self.be.stream()))
+            self.my_launches += 3
+        else:
+            acts = m.sample_actions(self.temp_threshold)
+            self.my_launches += 1
+        m.advance(acts)
+        self.my_launches += 1
+        self.move += 1
+        return acts
+
+    def play_move(self, wave_timer=None) -> torch.Tensor:
+        self.search(wave_timer)
+        return self.finish_move()
+
+    def play_episode(self, max_moves: int | None = None) -> int:
+        """Play until every game is over (or ``max_moves``); returns the number of moves played."""
+        limit = self.max_moves if max_moves is None else min(max_moves, self.max_moves)
+        while self.move < limit:
+            self.play_move()
+            if self.move % 16 == 0 or self.move == limit:
+                st = self.mcts.status()
+                if bool((st[:, 2] != 0).any()):
+                    self.mcts.raise_on_faults()
+                if bool((st[:, 4] != 0).all()):
+                    break
+        return self.move
+
+    # ---- host-buffer step (the end-to-end form measured by bench.py) ---------------------------------
+    def step_host(self, roots_host: torch.Tensor, counts_host: torch.Tensor, actions_host: torch.Tensor,
+                  next_roots_host: torch.Tensor) -> None:
+        """getActionProb + action choice + to_next_state for G games given as pinned HOST buffers: copies the root
+        states in, searches, copies visit counts, actions and next states out, and synchronises."""
+        dev_roots = roots_host.to(self.be.device, non_blocking=True)
+        self.mcts.set_roots(dev_roots)
+        self.search()
+        stats = self.mcts.root_stats()
+        acts = self.mcts.sample_actions(self.temp_threshold)
+        self.mcts.advance(acts)
+        counts_host.copy_(stats["counts"], non_blocking=True)
+        actions_host.copy_(acts, non_blocking=True)
+        next_roots_host.copy_(self.mcts.roots(), non_blocking=True)
+        self.my_launches += 5
+        if self.be.is_cuda:
+            torch.cuda.current_stream(self.be.device).synchronize()
+        self.move += 1
+
+    # ---- training examples (Coach.py:74-90) ----------------------------------------------------------
+    def examples(self, games=None, fix_alignment: bool = False, expand_symmetries: bool = True):
+        """-> (planes int64 [E,4,7,7], pi float64 [E,343], v float64 [E]) for the selected finished games, in the
+        reference's order: per game, per move, the 36 symmetric forms (Coach.py:77-78,89-90).
+
+        Value targets follow Coach.py:89-90.  The reference extends ``players`` by the cumulative example count
+        (Coach.py:79), so entry i of the zip pairs example i with players[i] where players = [P1]*36 + [P2]*72 +
+        [P1]*108 + ...; that quirk is reproduced unless ``fix_alignment``."""
+        assert self.record
+        n_moves = self.move
+        st_all = self.ex_states[:n_moves].cpu().numpy().view(STATE_DTYPE).reshape(n_moves, self.G)
+        final = self.mcts.roots().cpu().numpy().view(STATE_DTYPE).reshape(self.G)
+        games = range(self.G) if games is None else games
+        out_planes, out_pi, out_v = [], [], []
+        value_of = {0: 0.0, 1: 1e-4, 2: 1.0, 3: -1.0}
+        for g in games:
+            played = int((self.ex_actions[:n_moves, g] >= 0).sum())
+            if played == 0:
+                continue
+            states = torch.from_numpy(np.ascontiguousarray(st_all[:played, g]).view(np.uint8).reshape(played, 64)).to(self.be.device)
+            planes = rules.planes(states, dtype=torch.int64, backend=self.be)
+            counts = self.ex_counts[:played, g].to(torch.float64)
+            moves = torch.arange(played, device=self.be.device)
+            temp1 = (moves + 1) < self.temp_threshold
+            pi = counts / counts.sum(dim=1, keepdim=True)
+            acts = self.ex_actions[:played, g].long()
+            onehot = torch.zeros_like(pi)
+            onehot[moves, acts] = 1.0
+            pi = torch.where(temp1[:, None], pi, onehot)
+            if expand_symmetries:
+                planes = rules.symmetries(planes.contiguous(), backend=self.be).reshape(-1, 4, 7, 7)
+                pi = rules.symmetries(pi.reshape(played, 7, 7, 7).contiguous(), backend=self.be).reshape(-1, 343)
+                per = 36
+            else:
+                per = 1
+            # side to move of each recorded state vs the side to move at the end
+            movers = np.where(st_all[:played, g]["player"] == 0, 1, -1)
+            end_player = 1 if final[g]["player"] == 0 else -1
+            result = value_of[int(final[g]["outcome"])]
+            if fix_alignment or per == 1:
+                players = np.repeat(movers, per)
+            else:
+                players = np.concatenate([np.full(per * (i + 1), movers[i]) for i in range(played)])[: per * played]
+            v = np.where(players == end_player, result, -result)
+            out_planes.append(planes.cpu().numpy())
+            out_pi.append(pi.cpu().numpy())
+            out_v.append(v.astype(np.float64))
+        if not out_planes:
+            return np.zeros((0, 4, 7, 7), np.int64), np.zeros((0, 343)), np.zeros(0)
+        return np.concatenate(out_planes), np.concatenate(out_pi), np.concatenate(out_v)

@@ -90,6 +90,11 @@ IFX_API int ifx_rules_planes(const ifx_state* states, const int32_t* sym, int64_
 IFX_API int ifx_rules_symmetries(const void* in, int64_t n, int channels, int elem_size, void* out,
                                  void* stream);
 
+/* rotate / translate / random_symmetry of arbitrary board-like arrays (InflexionGame.py:115-196):
+ * out[i] = translate(rotate(in[i], k), shift, axis) with sym[i] = k + 6*shift + 42*axis (0 <= sym < 126). */
+IFX_API int ifx_rules_transform(const void* in, const int32_t* sym, int64_t n, int channels, int elem_size,
+                                void* out, void* stream);
+
 /* score / piece_count_diff / power_diff / total_power (InflexionGame.py:198-199, 312-323, 347):
  * info[i] = { score for side to move, power_diff for side to move, total_power, number of valid actions }. */
 IFX_API int ifx_rules_info(const ifx_state* states, int64_t n, int32_t* info /* [n][4] */, void* stream);
@@ -100,6 +105,8 @@ IFX_API int ifx_rules_mask_step_host(const ifx_state* states_in, const int32_t* 
                                      uint64_t* masks, ifx_state* states_out, int32_t* status);
 IFX_API int ifx_rules_planes_host(const ifx_state* states, const int32_t* sym, int64_t n, int dtype, void* out);
 IFX_API int ifx_rules_symmetries_host(const void* in, int64_t n, int channels, int elem_size, void* out);
+IFX_API int ifx_rules_transform_host(const void* in, const int32_t* sym, int64_t n, int channels, int elem_size,
+                                     void* out);
 IFX_API int ifx_rules_info_host(const ifx_state* states, int64_t n, int32_t* info);
 
 /* ---- batched MCTS: one warp per game tree ----------------------------------------------------- */
