@@ -1,6 +1,7 @@
 // Rules kernels (one thread per state) and their C ABI.  See include/ifx_b200.h for the contract.
 #include "ifx_rules.cuh"
 #include "ifx_host.cuh"
+#include "ifx_philox.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // per-state cores
@@ -27,6 +28,28 @@ IFX_HD void rules_info_of(const ifx_state& s, int32_t* info) {
   info[1] = 2 * own_pw - tot;                      // power_diff for the side to move (:312-317)
   info[2] = tot;                                   // total_power (:347)
   info[3] = ifx_num_valid(s);
+}
+
+// index of the k-th (0-based) set bit of m
+IFX_HD int rules_nth_bit(uint64_t m, int k) {
+  while (k-- > 0) m &= m - 1;
+  int idx = 0;
+  while (!((m >> idx) & 1ull)) ++idx;
+  return idx;
+}
+
+// uniform-random valid action, drawn as RandomPlayer does (InflexionPlayers.py:24-34: choice over the valid
+// actions in ascending order): the (w0 % count)-th valid action, Philox counter = (stream, step, 0, 3).
+IFX_HD int rules_random_action_of(const ifx_state& s, uint64_t seed, uint32_t stream, uint32_t step) {
+  if (s.outcome != IFX_ONGOING) return -1;
+  const uint64_t own = ifx_own(s), spawn = ifx_spawn_mask(s);
+  const int n_own = ifx_popc64(own), n_sp = ifx_popc64(spawn);
+  const int count = 6 * n_own + n_sp;
+  if (count == 0) return -1;
+  const IfxRand4 r = ifx_philox(seed, stream, step, 0u, 3u);
+  int k = (int)(r.w[0] % (uint32_t)count);
+  if (k < 6 * n_own) { const int m = k / n_own; return m * IFX_CELLS + rules_nth_bit(own, k - m * n_own); }
+  return IFX_SPAWN * IFX_CELLS + rules_nth_bit(spawn, k - 6 * n_own);
 }
 
 // value of plane c at (symmetry-mapped) cell, as float
@@ -133,6 +156,17 @@ __global__ void rules_transform_kernel(const T* __restrict__ in, const int32_t* 
   const int64_t i = e / per;
   const int rem = (int)(e - i * per), c = rem / IFX_CELLS, cell = rem - c * IFX_CELLS;
   out[e] = __ldg(in + (i * channels + c) * IFX_CELLS + ifx_sym_src(__ldg(sym + i), cell));
+}
+
+__global__ void rules_random_actions_kernel(const ifx_state* __restrict__ states, int64_t n, uint64_t seed,
+                                            uint32_t step, int32_t* __restrict__ actions) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  union { ifx_state s; uint4 q[4]; } a;
+  const uint4* p = reinterpret_cast<const uint4*>(states + i);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) a.q[c] = __ldg(p + c);
+  actions[i] = rules_random_action_of(a.s, seed, a.s.tag, step);
 }
 
 __global__ void rules_info_kernel(const ifx_state* __restrict__ states, int64_t n, int32_t* __restrict__ info) {
@@ -242,6 +276,19 @@ int ifx_rules_transform(const void* in, const int32_t* sym, int64_t n, int chann
   else
     rules_transform_kernel<unsigned long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const unsigned long long*)in, sym, n, channels, (unsigned long long*)out);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_rules_random_actions(const ifx_state* states, int64_t n, uint64_t seed, uint32_t step, int32_t* actions,
+                             void* stream) {
+  if (n < 0 || (n > 0 && (!states || !actions))) return IFX_E_ARG;
+  if (n == 0) return IFX_OK;
+#ifdef IFX_HOSTSIM
+  for (int64_t i = 0; i < n; ++i) actions[i] = rules_random_action_of(states[i], seed, states[i].tag, step);
+  return IFX_OK;
+#else
+  rules_random_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(states, n, seed, step, actions);
   return ifx_after_launch();
 #endif
 }

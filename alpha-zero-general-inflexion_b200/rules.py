@@ -66,6 +66,15 @@ def transform(x: torch.Tensor, sym: torch.Tensor, backend: Backend | None = None
     return out
 
 
+def random_actions(states: torch.Tensor, seed: int, step: int, backend: Backend | None = None) -> torch.Tensor:
+    """RandomPlayer for every state: uniform over the valid actions (stream = state tag) -> int32 [S], -1 = game over."""
+    be = backend or default_backend()
+    out = be.empty((states.shape[0],), torch.int32)
+    be.check(be.dll.ifx_rules_random_actions(_ptr(states), states.shape[0], int(seed) & (2 ** 64 - 1), int(step),
+                                             _ptr(out), be.stream()))
+    return out
+
+
 def info(states: torch.Tensor, backend: Backend | None = None) -> torch.Tensor:
     """-> int32 [S,4]: score, power_diff (side to move), total_power, number of valid actions."""
     be = backend or default_backend()

@@ -99,6 +99,11 @@ IFX_API int ifx_rules_transform(const void* in, const int32_t* sym, int64_t n, i
  * info[i] = { score for side to move, power_diff for side to move, total_power, number of valid actions }. */
 IFX_API int ifx_rules_info(const ifx_state* states, int64_t n, int32_t* info /* [n][4] */, void* stream);
 
+/* RandomPlayer.play for every state (InflexionPlayers.py:24-34): a uniform draw over the valid actions in
+ * ascending order, from Philox(seed; states[i].tag, step, 0, 3); -1 for finished games / no valid action. */
+IFX_API int ifx_rules_random_actions(const ifx_state* states, int64_t n, uint64_t seed, uint32_t step,
+                                     int32_t* actions, void* stream);
+
 /* Host-buffer forms of the above (plain host pointers; copies in, launches, copies out, synchronises).
  * These are what the object-per-game drop-in API (InflexionGame.to_next_state etc.) calls. */
 IFX_API int ifx_rules_mask_step_host(const ifx_state* states_in, const int32_t* actions, int64_t n,

@@ -70,10 +70,63 @@ def test_random_reachable_states_small(backend):
     _random_states_check(backend, 3000, seed=1)
 
 
+def _oracle_check_transitions(states_np, acts_np, masks_np, nxt_np):
+    b, p, t = unpack_boards(states_np), players_of(states_np), states_np["turn"].astype(np.int64)
+    assert np.array_equal(unpack_masks(masks_np), R.batch_valid_mask(b, p))
+    nb, npl, nt, out = R.batch_step(b, p, t, acts_np)
+    assert np.array_equal(unpack_boards(nxt_np), nb)
+    assert np.array_equal(nxt_np["outcome"], out) and np.array_equal(nxt_np["turn"], nt)
+    assert np.array_equal(players_of(nxt_np), npl)
+    assert np.array_equal(nxt_np["total_power"], np.abs(nb).sum(axis=1))
+
+
+def _device_playouts(backend, n, seed, check_every, check_count):
+    """Uniform-random valid play on the device from the start position for a uniform number of plies in
+    [0, 343] (BASELINE config 2); a strided sample of the transitions is checked against the oracle on the way."""
+    from oracle.inflexion_mcts import philox4x32
+    rng = np.random.default_rng(seed)
+    plies = torch.from_numpy(rng.integers(0, 344, size=n)).to(backend.device)
+    states = backend.states_tensor(pack_states(np.zeros((n, 49), dtype=np.int64), 1, 0, 0, 343, tags=np.arange(n)))
+    for t in range(343):
+        acts = rules.random_actions(states, seed, t, backend=backend)
+        masks, nxt, status = rules.mask_step(states, acts, backend=backend)
+        if t % check_every == 0:
+            idx = torch.from_numpy(rng.choice(n, size=min(check_count, n), replace=False)).to(backend.device)
+            s_np, a_np = to_np_states(states[idx]), acts[idx].cpu().numpy()
+            ok = a_np >= 0
+            _oracle_check_transitions(s_np[ok], a_np[ok], masks[idx].cpu().numpy()[ok], to_np_states(nxt[idx])[ok])
+            # the draw itself: the (w0 % count)-th valid action in ascending order
+            valid = unpack_masks(masks[idx].cpu().numpy())
+            for j in np.flatnonzero(ok)[:64]:
+                w0 = philox4x32((int(s_np["tag"][j]), t, 0, 3), (seed & 0xFFFFFFFF, seed >> 32))[0]
+                assert a_np[j] == np.flatnonzero(valid[j])[w0 % int(valid[j].sum())]
+        live = (plies > t) & (status == 0) & (nxt[:, 45] == 0)      # a game that just ended stays on its last position
+        states = torch.where(live[:, None], nxt, states)
+    return states
+
+
+def test_device_playouts_small(backend):
+    states = _device_playouts(backend, 2000, seed=11, check_every=7, check_count=500)
+    acts = rules.random_actions(states, 99, 0, backend=backend)
+    masks, nxt, status = rules.mask_step(states, acts, backend=backend)
+    assert int(status.abs().sum()) == 0
+    _oracle_check_transitions(to_np_states(states), acts.cpu().numpy(), masks.cpu().numpy(), to_np_states(nxt))
+
+
 @pytest.mark.gpu
 def test_random_reachable_states_1m(cuda_backend):
-    """BASELINE config 2: 1M random reachable states, move mask + step bit-exact."""
-    _random_states_check(cuda_backend, 1_000_000, seed=0)
+    """BASELINE config 2: 1M random reachable states, move mask + step bit-exact against the oracle."""
+    be = cuda_backend
+    states = _device_playouts(be, 1_000_000, seed=0, check_every=49, check_count=20000)
+    acts = rules.random_actions(states, 7, 0, backend=be)
+    masks, nxt, status = rules.mask_step(states, acts, backend=be)
+    assert int(status.abs().sum()) == 0
+    s_np = to_np_states(states)
+    assert s_np["turn"].max() >= 340 and (s_np["total_power"] > 48).any()
+    _oracle_check_transitions(s_np, acts.cpu().numpy(), masks.cpu().numpy(), to_np_states(nxt))
+    pl = rules.planes(nxt[:100000].contiguous(), dtype=torch.int64, backend=be).cpu().numpy()
+    n_np = to_np_states(nxt[:100000])
+    assert np.array_equal(pl, R.batch_planes(unpack_boards(n_np), players_of(n_np), n_np["turn"].astype(np.int64)))
 
 
 def test_ragged_sizes_and_empty(backend):
