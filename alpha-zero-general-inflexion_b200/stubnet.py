@@ -15,15 +15,17 @@ from __future__ import annotations
 import torch
 
 _MASK31 = (1 << 31) - 1
-_COEF = None
+_COEF = {}      # per device (a host->device copy is not allowed while a CUDA graph is being captured)
 
 
 def _coef(device):
-    global _COEF
-    if _COEF is None:
-        g = torch.Generator().manual_seed(20231018)
-        _COEF = torch.randint(1, 1 << 20, (196,), generator=g, dtype=torch.int64) | 1
-    return _COEF.to(device)
+    key = str(device)
+    if key not in _COEF:
+        if "cpu" not in _COEF:
+            g = torch.Generator().manual_seed(20231018)
+            _COEF["cpu"] = torch.randint(1, 1 << 20, (196,), generator=g, dtype=torch.int64) | 1
+        _COEF[key] = _COEF["cpu"].to(device)
+    return _COEF[key]
 
 
 def _mix(h):
@@ -47,7 +49,7 @@ def stub_policy_value(planes: torch.Tensor, mode: str = "float"):
     else:
         # a few large priors make the trees several plies deep, like a trained net's would
         peaked = torch.where((z >> 8) % 11 == 0, sharp * 64, sharp)
-        pi = peaked.to(torch.float32) / torch.tensor(1000003.0, dtype=torch.float32, device=x.device)
+        pi = peaked.to(torch.float32) / 1000003.0        # float32 / float32(1000003): one IEEE division
     hv = _mix(h ^ 0x5BD1E995)
     v = ((hv & 0xFFFF) - 32768).to(torch.float32) / 32768.0               # dyadic in [-1, 1)
     return pi, v

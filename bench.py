@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--sims", type=int, default=100, help="numMCTSSims per move")
     ap.add_argument("--net", default="default", choices=["default", "stub"],
                     help="default = the reference CNN (bf16 inference); stub = deterministic hash net (tree+rules only)")
+    ap.add_argument("--workload", default="selfplay", choices=["selfplay", "rules"],
+                    help="selfplay = the headline (BASELINE configs[2]); rules = the rules kernel alone (configs[1] shape)")
+    ap.add_argument("--states", type=int, default=4 * 1024 * 1024, help="states per launch for --workload rules")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -341,9 +344,67 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_rules(a):
+    """Rules kernel alone: valid-move mask + step for `states` random reachable positions per launch."""
+    import numpy as np
+    import torch
+    import inflexion_b200  # noqa: F401
+    from inflexion_b200 import rules
+    from inflexion_b200.backend import Backend
+    from inflexion_b200.state import pack_states
+    be = Backend.cuda(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    n = a.states
+    rng = np.random.default_rng(0)
+    plies = torch.from_numpy(rng.integers(0, 344, size=n)).to(be.device)
+    states = be.states_tensor(pack_states(np.zeros((n, 49), dtype=np.int64), 1, 0, 0, 343, tags=np.arange(n)))
+    for t in range(343):                                     # uniform-random reachable positions (config 2)
+        acts = rules.random_actions(states, 1, t, backend=be)
+        _, nxt, status = rules.mask_step(states, acts, want_masks=False, backend=be)
+        states = torch.where(((plies > t) & (status == 0) & (nxt[:, 45] == 0))[:, None], nxt, states)
+    acts = rules.random_actions(states, 2, 0, backend=be)
+    masks, nxt, status = (be.empty((n, 7), torch.int64), be.empty((n, 64), torch.uint8), be.empty((n,), torch.int32))
+    stream = be.stream()
+
+    def launch():
+        be.check(be.dll.ifx_rules_mask_step(states.data_ptr(), acts.data_ptr(), n, masks.data_ptr(), nxt.data_ptr(),
+                                            status.data_ptr(), stream))
+    for _ in range(max(a.warmup, 3)):
+        launch()
+    torch.cuda.synchronize()
+    evs = []
+    with ClockSampler(0) as clocks:
+        for _ in range(a.steps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); launch(); e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+    ms = [s.elapsed_time(e) for s, e in evs]
+    avg = sum(ms) / len(ms)
+    bytes_per_launch = 188 * n            # 64 B state in + 4 B action + 64 B state out + 56 B packed mask (SURVEY.md 8d)
+    gbs = bytes_per_launch / (avg * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "rules_states_per_sec", "value": n / (avg * 1e-3), "unit": "states/s", "n_gpus": 1, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": avg, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 bitboards", "data": "synthetic",
+        "config": {"workload": f"rules kernel: move mask + step, {n} random reachable states per launch "
+                               f"({bytes_per_launch / 1e6:.0f} MB per launch, larger than L2)"},
+        "roofline": {"kernel": "rules_mask_step_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": gbs / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "avg_launch_us": avg * 1e3, "min_launch_us": min(ms) * 1e3},
+        "gpu_launches": a.steps, "clocks": clocks.summary()}), flush=True)
+
+
 if __name__ == "__main__":
     args = parse_args()
-    if args.impl == "reference":
+    if args.workload == "rules":
+        run_rules(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -1,0 +1,94 @@
+"""Callers of the hot path with the reference's interfaces: Coach.executeEpisode, Arena, example files."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import inflexion_b200.backend as backend_mod
+from inflexion_b200.Arena import Arena
+from inflexion_b200.Coach import Coach
+from inflexion_b200.flags import PlayerColour
+from inflexion_b200.inflexion.InflexionGame import InflexionGame
+from inflexion_b200.inflexion.InflexionPlayers import GreedyPlayer, MCTSPlayer, RandomPlayer
+from inflexion_b200.MCTS import MCTS
+from inflexion_b200.stubnet import stub_policy_value
+from inflexion_b200.utils import dotdict
+from oracle.inflexion_mcts import PhiloxDraws, sample_action
+
+
+@pytest.fixture(autouse=True)
+def use_backend(backend, monkeypatch):
+    monkeypatch.setattr(backend_mod, "_DEFAULT", backend)
+    return backend
+
+
+class StubNet:
+    def __init__(self, mode="float"):
+        self.mode = mode
+
+    def predict(self, board):
+        pi, v = stub_policy_value(torch.from_numpy(np.ascontiguousarray(board))[None], self.mode)
+        return pi.numpy()[0], v.numpy()
+
+    def predict_batch(self, planes):
+        return stub_policy_value(planes, self.mode)
+
+
+@pytest.mark.parametrize("name", ["c_short_full", "d_short_full"])
+def test_execute_episode_reproduces_reference_examples(golden_dir, name, monkeypatch):
+    """Coach.executeEpisode over the drop-in classes == the examples the reference's Coach produced (same stub net,
+    same injected draws: the action sample of Coach.py:81 is replayed from the Philox uniform the golden run used)."""
+    g = np.load(os.path.join(golden_dir, f"mcts_{name}.npz"))
+    cpuct = int(g["cpuct"]) if bool(g["cpuct_is_int"]) else float(g["cpuct"])
+    args = dotdict({"numMCTSSims": int(g["sims"]), "cpuct": cpuct, "tempThreshold": int(g["temp_threshold"])})
+    game = InflexionGame(7, max_turns=int(g["max_turns"]), max_power=6)
+    draws, move = PhiloxDraws(int(g["seed"])), [0]
+
+    def choice(a, size=None, replace=True, p=None):
+        act = sample_action(np.asarray(p), draws.uniform(move[0]))
+        move[0] += 1
+        return act
+    monkeypatch.setattr(np.random, "choice", choice)
+    coach = Coach(game, StubNet(str(g["mode"])), args)
+    ex = coach.executeEpisode((game.restarted(), MCTS(StubNet(str(g["mode"])), args, seed=int(g["seed"]))))
+    assert len(ex) == len(g["ex_v"])
+    assert np.array_equal(np.array([e[0] for e in ex]), g["ex_planes"].astype(np.int64))
+    assert np.array([e[1] for e in ex], dtype=np.float64).tobytes() == g["ex_pi"].tobytes()
+    assert np.array([e[2] for e in ex], dtype=np.float64).tobytes() == g["ex_v"].tobytes()
+    assert isinstance(ex[0][1], list) and ex[0][0].dtype == np.int64 and ex[0][0].shape == (4, 7, 7)
+
+
+def test_arena_results_and_colour_split():
+    game = InflexionGame(7, max_turns=12, max_power=6)
+    np.random.seed(1)
+    arena = Arena(GreedyPlayer(), RandomPlayer(), game)
+    wins, draws = arena.playGame(PlayerColour.RED, PlayerColour.BLUE)
+    assert sum(wins.values()) + draws == 1 and all(isinstance(k, PlayerColour) for k in wins)
+    one, two, dr = arena.playGames(4)
+    assert one + two + dr == 4
+    mp = MCTSPlayer(MCTS(StubNet(), dotdict({"numMCTSSims": 6, "cpuct": 1.0}), seed=2))
+    one, two, dr = Arena(mp, RandomPlayer(), game).playGames(2)
+    assert one + two + dr == 2
+
+
+def test_example_file_format_roundtrip(tmp_path):
+    game = InflexionGame(7, max_turns=4, max_power=6)
+    args = dotdict({"numMCTSSims": 5, "cpuct": 1, "tempThreshold": 2, "checkpoint": str(tmp_path),
+                    "load_folder_file": (str(tmp_path), "checkpoint_0.pth.tar")})
+    coach = Coach(game, StubNet(), args)
+    np.random.seed(0)
+    ex = coach.executeEpisode((game.restarted(), MCTS(StubNet(), args, seed=1)))
+    from collections import deque
+    coach.trainExamplesHistory.append(deque(ex, maxlen=1000))
+    coach.saveTrainExamples(0)
+    path = os.path.join(tmp_path, "checkpoint_0.pth.tar.examples")
+    with open(path, "rb") as f:
+        hist = pickle.load(f)                                      # plain pickle, as the reference writes it
+    assert isinstance(hist, list) and isinstance(hist[0], deque) and len(hist[0]) == len(ex)
+    board, pi, v = hist[0][0]
+    assert board.shape == (4, 7, 7) and len(pi) == 343 and isinstance(v, float)
+    c2 = Coach(game, StubNet(), args)
+    c2.loadTrainExamples()
+    assert c2.skipFirstSelfPlay and len(c2.trainExamplesHistory[0]) == len(ex)
