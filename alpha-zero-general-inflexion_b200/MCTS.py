@@ -55,7 +55,7 @@ class MCTS:
         state["tag"] = 0
         if self._tree is None:
             self._tree = BatchedMCTS(1, sims, cpuct, seed=self._seed, backend=self._backend,
-                                     nodes_per_game=max(4096, 16 * sims) if sims <= 1024 else 16384)
+                                     nodes_per_game=min(16383, max(4096, 16 * sims)))
             self._tree.reset(state)
         else:
             self._tree.set_params(sims, cpuct)

@@ -23,7 +23,7 @@ class MctsConfig(C.Structure):
 
 
 class MctsLayout(C.Structure):
-    _fields_ = [(n, c_int64) for n in ("rows", "q64", "node_key", "node_ns", "hash", "free_stack", "per_game",
+    _fields_ = [(n, c_int64) for n in ("rows", "q64", "node_key", "node_head", "hash", "free_stack", "per_game",
                                         "path", "roots", "leaves", "total")]
 
 
@@ -49,6 +49,7 @@ PROTOTYPES = {
     "ifx_mcts_create": (c_int, [C.POINTER(MctsConfig), c_void_p, c_size_t, C.POINTER(c_void_p)]),
     "ifx_mcts_destroy": (None, [c_void_p]),
     "ifx_mcts_set_params": (c_int, [c_void_p, c_int32, c_float]),
+    "ifx_mcts_set_debug": (c_int, [c_void_p, c_void_p]),
     "ifx_mcts_reset_games": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_set_roots": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_wave": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -48,6 +48,14 @@
   IFX_D double ifx_dsqrt(double a) { return __dsqrt_rn(a); }
 #endif
 
+#ifdef IFX_HOSTSIM
+static inline uint32_t ifx_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float ifx_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#else
+IFX_D uint32_t ifx_f2u(float f) { return __float_as_uint(f); }
+IFX_D float ifx_u2f(uint32_t u) { return __uint_as_float(u); }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Per-lane variables and warp collectives.  On the device a LaneVar is one register per thread; in
 // the host simulation it is an array of 32 and the collectives loop.
@@ -87,6 +95,10 @@ static inline void lanes_bfly_fadd(LaneVar<float>& x, int mask) {
   for (int l = 0; l < 32; ++l) x[l] = t[l];
 }
 template <class T> static inline T lanes_bcast(const LaneVar<T>& x, int src) { return x[src]; }
+// out[l] = in[l + 1]  (lane 31 keeps its own value)
+static inline void lanes_shift_down(const LaneVar<uint32_t>& in, LaneVar<uint32_t>& out) {
+  for (int l = 0; l < 32; ++l) out[l] = in[l < 31 ? l + 1 : 31];
+}
 // maximum u; ties go to the LOWEST action index (sequential scan with strict '>' in MCTS.py:119-129)
 static inline void lanes_argmax(const LaneVar<float>& u, const LaneVar<int>& a, float* bu, int* ba) {
   float best = u[0]; int arg = a[0];
@@ -102,15 +114,21 @@ IFX_D void lanes_bfly_fadd(LaneVar<float>& x, int mask) {
   x.v = __fadd_rn(x.v, __shfl_xor_sync(0xffffffffu, x.v, mask));
 }
 template <class T> IFX_D T lanes_bcast(const LaneVar<T>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
+IFX_D void lanes_shift_down(const LaneVar<uint32_t>& in, LaneVar<uint32_t>& out) {
+  out.v = __shfl_down_sync(0xffffffffu, in.v, 1);
+}
+// Two REDUX operations instead of a five-step shuffle butterfly: floats map to unsigned keys that sort the
+// same way (with -0.0 folded onto +0.0, which compare equal), the maximum key is found with redux.max, and the
+// lowest action index among the lanes holding it with redux.min.
 IFX_D void lanes_argmax(const LaneVar<float>& u, const LaneVar<int>& a, float* bu, int* ba) {
-  float best = u.v; int arg = a.v;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    float ou = __shfl_xor_sync(0xffffffffu, best, off);
-    int oa = __shfl_xor_sync(0xffffffffu, arg, off);
-    if (ou > best || (ou == best && oa < arg)) { best = ou; arg = oa; }
-  }
-  *bu = best; *ba = arg;
+  uint32_t k = __float_as_uint(u.v);
+  k = (k == 0x80000000u) ? 0u : k;
+  k = (k & 0x80000000u) ? ~k : (k | 0x80000000u);
+  const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);
+  const uint32_t cand = (k == kmax) ? (uint32_t)a.v : 0xffffffffu;
+  const uint32_t amin = __reduce_min_sync(0xffffffffu, cand);
+  const uint32_t back = (kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax;
+  *bu = __uint_as_float(back); *ba = (int)amin;
 }
 #endif
 

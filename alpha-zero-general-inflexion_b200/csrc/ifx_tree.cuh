@@ -6,9 +6,17 @@
 // Numerics follow SURVEY.md appendix B exactly (numpy 2.x / NEP-50): float32 PUCT with separate
 // round-to-nearest operations, numpy's pairwise float32 sum for the prior renormalisation, and edge
 // values that are either float32 (came from the net) or Python floats (came from a terminal state).
+//
+// Latency structure (the kernel is bound by dependent HBM round trips, not by arithmetic): every phase
+// issues ALL of its loads before consuming any -- whole P/N/Q rows as 128-bit loads, the pending leaf, its
+// policy row, the path's edges -- and state that would cost a dependent load is carried in the per-game
+// record instead (root slot, next free slot, hash position of the pending leaf, the path itself, which
+// lives one level per lane in registers and is spilled to HBM only while a leaf waits for the net).
 #pragma once
 #include "ifx_rules.cuh"
 #include "ifx_philox.cuh"
+
+#define IFX_MAX_DEPTH 32           // one path level per lane
 
 struct alignas(16) IfxGame {       // 64 bytes per game
   int32_t sims_done;               // root-level search() calls finished in the current move (MCTS.py:45-46)
@@ -16,32 +24,60 @@ struct alignas(16) IfxGame {       // 64 bytes per game
   int32_t faults;                  // IFX_F_* bits
   int32_t move_idx;                // getActionProb calls so far (RNG coordinate)
   int32_t path_len;                // edges on the path to the pending leaf
-  int32_t free_top;                // free slots on the stack
+  int32_t free_top;                // free slots left on the stack (not counting next_slot)
   uint32_t game_id;                // RNG stream coordinate
   int32_t n_live;
   uint32_t n_visits, n_expand, n_term, n_sims;   // counters: V, E, terminal leaves, simulations
-  int32_t pad[4];
+  int32_t root_slot;               // node slot of the root, -1 while it is not expanded
+  int32_t next_slot;               // slot the next expansion will use (popped ahead of time), -1 = pool empty
+  int32_t leaf_hpos;               // hash position (first empty probe slot) found when the pending leaf missed
+  int32_t pad;
 };
 
 struct alignas(16) IfxKey { uint64_t k0, k1; };
+struct alignas(16) IfxF4 { float x, y, z, w; };
+struct alignas(16) IfxU4 { uint32_t x, y, z, w; };
+
+// One 32-bit word per edge in the N row:
+//   bits 0..16   visit count N(s,a)              (MCTS.py:27 Nsa)
+//   bits 17..30  child hint: node slot the edge led to last time (0x3FFF = none).  Only a hint -- the key of
+//                that slot is compared with the recomputed child key before it is trusted, because the
+//                reference's table is keyed by planes, not by (s,a)
+//   bit 31       Q of this edge is a Python float (kept in q64)
+//   0xFFFFFFFF   the action is not valid in this node (Vs[s][a] == 0, MCTS.py:109,120)
+#define IFX_N_TAG 0x80000000u
+#define IFX_N_COUNT 0x0001FFFFu
+#define IFX_N_HINT_SHIFT 17
+#define IFX_N_HINT_NONE 0x3FFFu
+#define IFX_N_INVALID 0xFFFFFFFFu
+#define IFX_N_FRESH (IFX_N_HINT_NONE << IFX_N_HINT_SHIFT)      // valid, unvisited, no hint
+IFX_HD uint32_t ifx_n_count(uint32_t raw) { return raw == IFX_N_INVALID ? 0u : (raw & IFX_N_COUNT); }
+
+// per-node header: Ns and the two square roots PUCT needs, refreshed whenever Ns changes (off the select path)
+struct alignas(16) IfxHead { int32_t ns; float sq_seen, sq_unseen; int32_t pad; };
+IFX_HD IfxHead ifx_head_of(int ns) {
+  IfxHead h; h.ns = ns; h.pad = 0;
+  h.sq_seen = (float)ifx_dsqrt((double)ns);                 // float32(math.sqrt(Ns))        MCTS.py:122
+  h.sq_unseen = (float)ifx_dsqrt((double)ns + 1e-8);        // float32(math.sqrt(Ns + EPS))  MCTS.py:125
+  return h;
+}
 
 struct TreeParams {
   float* rows;          // [G][C][3][352]  P | N | Q
   double* q64;          // [G][C][344]
   IfxKey* node_key;     // [G][C]
-  int32_t* node_ns;     // [G][C]
+  IfxHead* node_head;   // [G][C]  Ns + cached square roots
   IfxKey* hash;         // [G][H]
   uint16_t* free_stack; // [G][C]
   IfxGame* games;       // [G]
-  uint32_t* path;       // [G][maxd]   slot << 9 | action
+  IfxU4* path;          // [G][32]   {slot << 9 | action, N word, Q bits, Ns} per level (valid while a leaf is pending)
   ifx_state* roots;     // [G]
   ifx_state* leaves;    // [G]
   int32_t G, C, H, maxd, num_sims, logits;
+  uint64_t* debug;      // optional [G][4]: wave start / end (globaltimer ns), deepest level, hash probes
   float cpuct;
   uint64_t seed;
 };
-
-#define IFX_N_TAG 0x80000000u     // bit 31 of an N entry: Q of this edge is a Python float (kept in q64)
 
 IFX_HD uint32_t ifx_hash_key(uint64_t k0, uint64_t k1) {
   uint64_t h = k0 * 0x9E3779B97F4A7C15ull ^ (k1 + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
@@ -53,8 +89,28 @@ IFX_HD float* tree_row(const TreeParams& P, int g, int slot, int which) {
   return P.rows + (((int64_t)g * P.C + slot) * 3 + which) * IFX_ROW;
 }
 
+IFX_HD bool tree_action_bit(uint64_t own, uint64_t spawn, int a) {
+  const int m = a / IFX_CELLS, cell = a - m * IFX_CELLS;
+  return ((m == IFX_SPAWN ? spawn : own) >> cell) & 1ull;
+}
+
+// validity of the four consecutive actions a .. a+3 (a % 4 == 0) as bits 0..3; planes are 49 cells long, so a
+// group can straddle two move types
+IFX_HD uint32_t tree_valid4(uint64_t own, uint64_t spawn, int a) {
+  if (a >= IFX_ACTIONS) return 0u;
+  const int m = a / IFX_CELLS, c = a - m * IFX_CELLS;
+  const uint64_t cur = m == IFX_SPAWN ? spawn : own;
+  uint32_t bits = (uint32_t)(cur >> c) & 0xFu;             // masks are 49 bits wide: cells beyond 48 read 0
+  if (c > IFX_CELLS - 4 && m < IFX_SPAWN) {                // the tail of the group belongs to move type m+1
+    const uint64_t nxt = (m + 1 == IFX_SPAWN) ? spawn : own;
+    bits |= ((uint32_t)nxt << (IFX_CELLS - c)) & 0xFu;
+  }
+  return bits;
+}
+
 // ---- hash (open addressing, linear probing, never deleted from: rebuilt when nodes are reclaimed) ----
-IFX_D int tree_hash_find(const TreeParams& P, int g, uint64_t k0, uint64_t k1) {
+// returns the slot, or -1; *miss_pos = position of the first empty entry of the probe sequence (insert point)
+IFX_D int tree_hash_find(const TreeParams& P, int g, uint64_t k0, uint64_t k1, int* miss_pos) {
   const IfxKey* tab = P.hash + (int64_t)g * P.H;
   const uint32_t h = ifx_hash_key(k0, k1);
   for (int probe = 0; probe < P.H; probe += 32) {
@@ -67,100 +123,125 @@ IFX_D int tree_hash_find(const TreeParams& P, int g, uint64_t k0, uint64_t k1) {
     }
     const uint32_t mm = lanes_ballot(match), me = lanes_ballot(empty);
     if (mm && (!me || ifx_ffs32(mm) < ifx_ffs32(me))) return lanes_bcast(slot, ifx_ffs32(mm) - 1);
-    if (me) return -1;
+    if (me) { *miss_pos = (int)((h + probe + ifx_ffs32(me) - 1) & (P.H - 1)); return -1; }
   }
+  *miss_pos = -1;
   return -1;
 }
 
-IFX_D bool tree_hash_insert(const TreeParams& P, int g, uint64_t k0, uint64_t k1, int slot) {
-  IfxKey* tab = P.hash + (int64_t)g * P.H;
-  const uint32_t h = ifx_hash_key(k0, k1);
-  for (int probe = 0; probe < P.H; probe += 32) {
-    LaneVar<int> empty;
-    IFX_FOR_LANES(l) { empty[l] = tab[(h + probe + l) & (P.H - 1)].k0 == IFX_KEY_EMPTY ? 1 : 0; }
-    const uint32_t me = lanes_ballot(empty);
-    if (me) {
-      if (IFX_LANE0) {
-        IfxKey e; e.k0 = k0; e.k1 = k1 | ((uint64_t)slot << 50);
-        tab[(h + probe + ifx_ffs32(me) - 1) & (P.H - 1)] = e;
-      }
-      IFX_SYNCWARP();
-      return true;
-    }
-  }
-  return false;
-}
-
 // ---- one edge of the backup (MCTS.py:136-142 under NEP-50 promotion) ----
-IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, double v, bool v_is32) {
+// (raw N, Q32) were loaded ahead of time; q64 is touched only for Python-float edges.  `child` (>= 0) refreshes
+// the edge's child hint.
+IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, uint32_t raw, float q32, double v, bool v_is32,
+                             int child) {
   uint32_t* nrow = reinterpret_cast<uint32_t*>(tree_row(P, g, slot, 1));
   float* qrow = tree_row(P, g, slot, 2);
   double* q64 = P.q64 + ((int64_t)g * P.C + slot) * 344 + a;
-  const uint32_t raw = nrow[a];
-  const uint32_t n = raw & ~IFX_N_TAG;
+  const uint32_t n = raw & IFX_N_COUNT;
   const bool q_is64 = (raw & IFX_N_TAG) != 0;
+  const uint32_t hint = child >= 0 ? ((uint32_t)child << IFX_N_HINT_SHIFT) : (raw & (IFX_N_HINT_NONE << IFX_N_HINT_SHIFT));
+  bool new_is64;
   if (n == 0) {                                    // first visit: Q = v, same kind
-    if (v_is32) { qrow[a] = (float)v; nrow[a] = 1u; }
-    else { *q64 = v; qrow[a] = (float)v; nrow[a] = 1u | IFX_N_TAG; }
+    new_is64 = !v_is32;
+    if (new_is64) *q64 = v;
+    qrow[a] = (float)v;
   } else if (q_is64 && !v_is32) {                  // Python float with Python float: float64 throughout
     const double q = ifx_ddiv(ifx_dadd(ifx_dmul((double)n, *q64), v), (double)(n + 1));
-    *q64 = q; qrow[a] = (float)q; nrow[a] = (n + 1) | IFX_N_TAG;
+    *q64 = q; qrow[a] = (float)q; new_is64 = true;
   } else if (!q_is64) {                            // float32 Q: everything rounds to float32
-    const float q = ifx_fdiv(ifx_fadd(ifx_fmul((float)n, qrow[a]), (float)v), (float)(n + 1));
-    qrow[a] = q; nrow[a] = n + 1;
+    qrow[a] = ifx_fdiv(ifx_fadd(ifx_fmul((float)n, q32), (float)v), (float)(n + 1));
+    new_is64 = false;
   } else {                                         // Python-float Q meets a float32 value: N*Q in float64, then float32
-    const float q = ifx_fdiv(ifx_fadd((float)ifx_dmul((double)n, *q64), (float)v), (float)(n + 1));
-    qrow[a] = q; nrow[a] = n + 1;
+    qrow[a] = ifx_fdiv(ifx_fadd((float)ifx_dmul((double)n, *q64), (float)v), (float)(n + 1));
+    new_is64 = false;
   }
+  nrow[a] = (n + 1) | hint | (new_is64 ? IFX_N_TAG : 0u);
 }
 
-// back `v` (the value returned by the deepest search() call) up the first `depth` edges of the path
-IFX_D void tree_backup(const TreeParams& P, int g, int depth, double v, bool v_is32) {
-  const uint32_t* path = P.path + (int64_t)g * P.maxd;
-  IFX_SYNCWARP();
+// The path lives one level per lane (lane L holds edge L) as {slot << 9 | action, N word, Q bits, Ns}: the
+// edge statistics were in registers when the edge was selected and nothing else touches this game's tree
+// before its backup, so the backup needs no loads of its own.
+// Back `v` (the value returned by the deepest search() call) up the first `depth` edges of the path; levels
+// are independent: distinct nodes (the turn strictly grows along a path).  `leaf_slot` is the node the last
+// edge leads to (-1: terminal state, no node).
+IFX_D void tree_backup_apply(const TreeParams& P, int g, int depth, const LaneVar<IfxU4>& path, double v, bool v_is32,
+                             int leaf_slot) {
+  LaneVar<uint32_t> edge, below;
+  IFX_FOR_LANES(l) { edge[l] = path[l].x; }
+  lanes_shift_down(edge, below);                            // path entry one level deeper
   IFX_FOR_LANES(l) {
-    for (int L = l; L < depth; L += 32) {          // levels are independent: distinct nodes (turn strictly grows)
-      const uint32_t e = path[L];
-      const int slot = (int)(e >> 9), a = (int)(e & 511u);
-      const double vl = ((depth - 1 - L) & 1) ? -v : v;     // each level returns -v to its parent (MCTS.py:145)
-      tree_update_edge(P, g, slot, a, vl, v_is32);
-      P.node_ns[(int64_t)g * P.C + slot] += 1;              // MCTS.py:144
+    if (l < depth) {
+      const int slot = (int)(edge[l] >> 9), a = (int)(edge[l] & 511u);
+      const double vl = ((depth - 1 - l) & 1) ? -v : v;     // each level returns -v to its parent (MCTS.py:145)
+      const int child = l + 1 < depth ? (int)(below[l] >> 9) : leaf_slot;
+      tree_update_edge(P, g, slot, a, path[l].y, ifx_u2f(path[l].z), vl, v_is32, child);
+      P.node_head[(int64_t)g * P.C + slot] = ifx_head_of((int)path[l].w + 1);               // MCTS.py:144
     }
   }
   IFX_SYNCWARP();
 }
 
 // ---- PUCT arg-max over the valid actions of one node (MCTS.py:114-129) ----
-IFX_D int tree_select(const TreeParams& P, int g, int slot, const ifx_state& st) {
+// The three rows are fetched whole with 128-bit loads (lane l owns actions 4l+128j .. +3) before any use;
+// validity comes with the N row (IFX_N_INVALID), the square roots with the node header.
+// Returns the action (or -1) and the raw N word of the chosen edge (it carries the child hint).
+struct RowRegs { LaneVar<IfxF4> p0, p1, p2, q0, q1, q2; LaneVar<IfxU4> n0, n1, n2; IfxHead head; IfxKey key; };
+
+IFX_D void tree_rows_load(const TreeParams& P, int g, int slot, RowRegs& R) {
   const float* prow = tree_row(P, g, slot, 0);
-  const uint32_t* nrow = reinterpret_cast<const uint32_t*>(tree_row(P, g, slot, 1));
+  const float* nrow = tree_row(P, g, slot, 1);
   const float* qrow = tree_row(P, g, slot, 2);
-  const int ns = P.node_ns[(int64_t)g * P.C + slot];
-  const float sq_seen = (float)ifx_dsqrt((double)ns);
-  const float sq_unseen = (float)ifx_dsqrt((double)ns + 1e-8);
-  const uint64_t own = ifx_own(st), spawn = ifx_spawn_mask(st);
-  LaneVar<float> bu; LaneVar<int> ba;
   IFX_FOR_LANES(l) {
-    float best = -INFINITY; int arg = 0x7fffffff;
-#pragma unroll
-    for (int j = 0; j < 11; ++j) {
-      const int a = l + 32 * j;
-      if (a < IFX_ACTIONS) {
-        const int m = a / IFX_CELLS, cell = a - m * IFX_CELLS;
-        if (((m == IFX_SPAWN ? spawn : own) >> cell) & 1ull) {
-          const float cp = ifx_fmul(P.cpuct, prow[a]);
-          const uint32_t n = nrow[a] & ~IFX_N_TAG;
-          const float u = n ? ifx_fadd(qrow[a], ifx_fdiv(ifx_fmul(cp, sq_seen), (float)(1u + n)))
-                            : ifx_fmul(cp, sq_unseen);
-          if (u > best) { best = u; arg = a; }              // ascending a within the lane: strict '>' keeps the lowest
-        }
-      }
+    const int i = 4 * l;
+    R.p0[l] = *reinterpret_cast<const IfxF4*>(prow + i);
+    R.n0[l] = *reinterpret_cast<const IfxU4*>(nrow + i);
+    R.q0[l] = *reinterpret_cast<const IfxF4*>(qrow + i);
+    R.p1[l] = *reinterpret_cast<const IfxF4*>(prow + i + 128);
+    R.n1[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 128);
+    R.q1[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 128);
+    if (i + 256 < IFX_ROW) {
+      R.p2[l] = *reinterpret_cast<const IfxF4*>(prow + i + 256);
+      R.n2[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 256);
+      R.q2[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 256);
+    } else {
+      const IfxF4 zf = {0.f, 0.f, 0.f, 0.f};
+      const IfxU4 zu = {IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID};
+      R.p2[l] = zf; R.q2[l] = zf; R.n2[l] = zu;
     }
-    bu[l] = best; ba[l] = arg;
+  }
+  R.head = P.node_head[(int64_t)g * P.C + slot];
+  R.key = P.node_key[(int64_t)g * P.C + slot];
+}
+
+IFX_D int tree_select(const TreeParams& P, const RowRegs& R, uint32_t* chosen_raw, float* chosen_q) {
+  const float sq_seen = R.head.sq_seen, sq_unseen = R.head.sq_unseen;
+  LaneVar<float> bu, bq; LaneVar<int> ba; LaneVar<uint32_t> braw;
+  IFX_FOR_LANES(l) {
+    float best = -INFINITY, qsel = 0.0f; int arg = 0x7fffffff; uint32_t raw = 0;
+    // ascending action order inside the lane, strict '>' keeps the lowest index on ties
+#define IFX_PUCT(PV, NV, QV, A)                                                                       \
+    do { if ((NV) != IFX_N_INVALID) {                                                                 \
+        const float cp = ifx_fmul(P.cpuct, (PV));                                                     \
+        const uint32_t n_ = (NV) & IFX_N_COUNT;                                                       \
+        const float u = n_ ? ifx_fadd((QV), ifx_fdiv(ifx_fmul(cp, sq_seen), (float)(1u + n_)))        \
+                           : ifx_fmul(cp, sq_unseen);                                                 \
+        if (u > best) { best = u; arg = (A); raw = (NV); qsel = (QV); } } } while (0)
+#define IFX_PUCT4(PV, NV, QV, BASE)                                                                   \
+    IFX_PUCT(PV.x, NV.x, QV.x, (BASE)); IFX_PUCT(PV.y, NV.y, QV.y, (BASE) + 1);                       \
+    IFX_PUCT(PV.z, NV.z, QV.z, (BASE) + 2); IFX_PUCT(PV.w, NV.w, QV.w, (BASE) + 3)
+    IFX_PUCT4(R.p0[l], R.n0[l], R.q0[l], 4 * l);
+    IFX_PUCT4(R.p1[l], R.n1[l], R.q1[l], 4 * l + 128);
+    IFX_PUCT4(R.p2[l], R.n2[l], R.q2[l], 4 * l + 256);
+#undef IFX_PUCT4
+#undef IFX_PUCT
+    bu[l] = best; ba[l] = arg; braw[l] = raw; bq[l] = qsel;
   }
   float u; int a;
   lanes_argmax(bu, ba, &u, &a);
-  return a == 0x7fffffff ? -1 : a;
+  if (a == 0x7fffffff) return -1;
+  *chosen_raw = lanes_bcast(braw, (a & 127) >> 2);          // the lane that owns action a
+  *chosen_q = lanes_bcast(bq, (a & 127) >> 2);
+  return a;
 }
 
 // ---- numpy's pairwise float32 sum of a 343-vector held in `buf` ----
@@ -190,47 +271,93 @@ IFX_D float tree_pairwise_sum343(const float* buf) {
   return lanes_bcast(r, 0);
 }
 
+// policy row of the pending leaf, fetched ahead of use in the row layout (lane l: actions 4l+128j .. +3)
+struct PolicyRegs { LaneVar<IfxF4> p[3]; };
+
+IFX_D void tree_policy_load(const float* pi, bool aligned, PolicyRegs& R) {
+  IFX_FOR_LANES(l) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      IfxF4 v = {0.f, 0.f, 0.f, 0.f};
+      if (aligned) {                                        // padded rows (stride % 4 == 0): one 128-bit load
+        if (i < IFX_ROW) v = *reinterpret_cast<const IfxF4*>(pi + i);
+      } else {
+        if (i < IFX_ACTIONS) v.x = pi[i];
+        if (i + 1 < IFX_ACTIONS) v.y = pi[i + 1];
+        if (i + 2 < IFX_ACTIONS) v.z = pi[i + 2];
+        if (i + 3 < IFX_ACTIONS) v.w = pi[i + 3];
+      }
+      R.p[j][l] = v;
+    }
+  }
+}
+
 // ---- expansion of the pending leaf (MCTS.py:89-112) ----
 // returns the slot, or -1 with a fault bit set
-IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, const float* pi, float* buf) {
+IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, const PolicyRegs& R, float* buf) {
   const uint64_t own = ifx_own(leaf), spawn = ifx_spawn_mask(leaf);
+  LaneVar<uint32_t> vbits;                                  // validity of the lane's 12 actions (4 bits per group)
+  LaneVar<IfxF4> m0, m1, m2;                                // policies *= valids (MCTS.py:95)
   IFX_FOR_LANES(l) {
-    for (int a = l; a < IFX_ROW; a += 32) {
-      float p = 0.0f;
-      if (a < IFX_ACTIONS) {
-        const int m = a / IFX_CELLS, cell = a - m * IFX_CELLS;
-        if (((m == IFX_SPAWN ? spawn : own) >> cell) & 1ull) p = pi[a];      // policies *= valids
-      }
-      buf[a] = p;
+    uint32_t vb = 0;
+    IfxF4 mv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      const uint32_t b = tree_valid4(own, spawn, i);
+      vb |= b << (4 * j);
+      IfxF4 v = R.p[j][l];
+      v.x = (b & 1u) ? v.x : 0.0f; v.y = (b & 2u) ? v.y : 0.0f;
+      v.z = (b & 4u) ? v.z : 0.0f; v.w = (b & 8u) ? v.w : 0.0f;
+      mv[j] = v;
+      if (i < IFX_ROW) *reinterpret_cast<IfxF4*>(buf + i) = v;
     }
+    vbits[l] = vb; m0[l] = mv[0]; m1[l] = mv[1]; m2[l] = mv[2];
   }
   IFX_SYNCWARP();
   float total = tree_pairwise_sum343(buf);                  // policies.sum()
   const bool uniform = !(total > 0.0f);                     // MCTS.py:98-107: all valid moves masked
   if (uniform) total = (float)ifx_num_valid(leaf);          // sum of 0/1 values is exact in any order
-  if (G.free_top <= 0) { G.faults |= IFX_F_POOL; return -1; }
-  const int slot = (int)P.free_stack[(int64_t)g * P.C + (G.free_top - 1)];
+  const int slot = G.next_slot;
+  if (slot < 0) { G.faults |= IFX_F_POOL; return -1; }
+  if (G.leaf_hpos < 0) { G.faults |= IFX_F_HASH; return -1; }
+  // pop the slot for the NEXT expansion now; the load is off the critical path
+  int next = -1;
+  if (G.free_top > 0) next = (int)P.free_stack[(int64_t)g * P.C + (G.free_top - 1)];
   float* prow = tree_row(P, g, slot, 0);
-  uint32_t* nrow = reinterpret_cast<uint32_t*>(tree_row(P, g, slot, 1));
+  float* nrow = tree_row(P, g, slot, 1);
   IFX_FOR_LANES(l) {
-    for (int a = l; a < IFX_ROW; a += 32) {
-      float p = buf[a];
-      if (uniform && a < IFX_ACTIONS) {
-        const int m = a / IFX_CELLS, cell = a - m * IFX_CELLS;
-        p = (((m == IFX_SPAWN ? spawn : own) >> cell) & 1ull) ? 1.0f : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      if (i < IFX_ROW) {
+        const uint32_t b = (vbits[l] >> (4 * j)) & 0xFu;
+        IfxF4 v = j == 0 ? m0[l] : (j == 1 ? m1[l] : m2[l]);
+        if (uniform) {                                      // policies = valids (MCTS.py:105)
+          v.x = (b & 1u) ? 1.0f : 0.0f; v.y = (b & 2u) ? 1.0f : 0.0f;
+          v.z = (b & 4u) ? 1.0f : 0.0f; v.w = (b & 8u) ? 1.0f : 0.0f;
+        }
+        v.x = ifx_fdiv(v.x, total); v.y = ifx_fdiv(v.y, total);         // policies /= sum
+        v.z = ifx_fdiv(v.z, total); v.w = ifx_fdiv(v.w, total);
+        *reinterpret_cast<IfxF4*>(prow + i) = v;
+        IfxU4 z;                                             // Vs[s] folded into the N row (MCTS.py:109)
+        z.x = (b & 1u) ? IFX_N_FRESH : IFX_N_INVALID; z.y = (b & 2u) ? IFX_N_FRESH : IFX_N_INVALID;
+        z.z = (b & 4u) ? IFX_N_FRESH : IFX_N_INVALID; z.w = (b & 8u) ? IFX_N_FRESH : IFX_N_INVALID;
+        *reinterpret_cast<IfxU4*>(nrow + i) = z;
       }
-      prow[a] = ifx_fdiv(p, total);                         // policies /= sum
-      nrow[a] = 0u;
     }
   }
   const uint64_t k0 = ifx_key0(leaf), k1 = ifx_key1(leaf);
-  if (!tree_hash_insert(P, g, k0, k1, slot)) { G.faults |= IFX_F_HASH; return -1; }
   if (IFX_LANE0) {
+    IfxKey e; e.k0 = k0; e.k1 = k1 | ((uint64_t)slot << 50);
+    P.hash[(int64_t)g * P.H + G.leaf_hpos] = e;             // the position the missed lookup ended on
     IfxKey k; k.k0 = k0; k.k1 = k1;
     P.node_key[(int64_t)g * P.C + slot] = k;
-    P.node_ns[(int64_t)g * P.C + slot] = 0;                 // MCTS.py:110
+    P.node_head[(int64_t)g * P.C + slot] = ifx_head_of(0);  // Ns[s] = 0 (MCTS.py:110)
   }
-  G.free_top -= 1;
+  if (G.free_top > 0) G.free_top -= 1;
+  G.next_slot = next;
   G.n_live += 1;
   G.n_expand += 1;
   IFX_SYNCWARP();
@@ -255,17 +382,33 @@ IFX_D void tree_write_nn_input(const TreeParams& P, const IfxGame& G, const ifx_
 }
 
 // ---- one wave for one game (see ifx_mcts_wave in include/ifx_b200.h) ----
+#ifdef IFX_HOSTSIM
+static inline uint64_t ifx_now_ns() { return 0; }
+#else
+IFX_D uint64_t ifx_now_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_t pi_stride, const float* nn_v,
                           float* nn_in, float* buf) {
+  const uint64_t dbg_t0 = P.debug ? ifx_now_ns() : 0;
+  int dbg_depth = 0, dbg_probes = 0;
+  // round trip 1: everything whose address is known up front, issued together (leaf / policy / value are
+  // speculative: they are only used when a leaf is pending, which is the common case)
   IfxGame G = P.games[g];
-  uint32_t* path = P.path + (int64_t)g * P.maxd;
+  const ifx_state leaf = P.leaves[g];
+  const float leaf_v = nn_v[g];
+  PolicyRegs pol;
+  const float* pi_row = nn_pi + (int64_t)g * pi_stride;
+  tree_policy_load(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, pol);
+  LaneVar<IfxU4> path;
+  IFX_FOR_LANES(l) { path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
   if (G.faults) return;
   if (G.pending) {
-    const ifx_state leaf = P.leaves[g];
-    const int slot = tree_expand(P, g, G, leaf, nn_pi + (int64_t)g * pi_stride, buf);
+    const int slot = tree_expand(P, g, G, leaf, pol, buf);
     if (slot >= 0) {
+      if (G.path_len == 0) G.root_slot = slot;              // the root itself was the leaf
       // search() of the leaf returns -v, v a float32 (MCTS.py:112; NNet.py:94)
-      tree_backup(P, g, G.path_len, -(double)nn_v[g], true);
+      tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot);
       G.sims_done += 1; G.n_sims += 1;
     }
     G.pending = 0;
@@ -273,35 +416,76 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   while (!G.faults && G.sims_done < P.num_sims) {
     ifx_state st = P.roots[g];
     int depth = 0;
+    int slot = G.root_slot;                                 // -1: the root is not expanded yet
+    bool verified = slot >= 0;                              // the cached root slot needs no key check
     for (;;) {
       if (st.outcome != IFX_ONGOING) {                      // MCTS.py:85-87: terminal, value is a Python number
-        tree_backup(P, g, depth, -ifx_outcome_value(st.outcome), false);
+        tree_backup_apply(P, g, depth, path, -ifx_outcome_value(st.outcome), false, -1);
         G.sims_done += 1; G.n_sims += 1; G.n_term += 1;
         break;
       }
-      const int slot = tree_hash_find(P, g, ifx_key0(st), ifx_key1(st));
+      const uint64_t k0 = ifx_key0(st), k1 = ifx_key1(st);
+      RowRegs rows;
+      int miss_pos = -1;
+      if (slot >= 0) {
+        // speculative: rows, header and key of the hinted slot in ONE round trip; the key decides whether the
+        // hint was right (the reference looks nodes up by planes, not by edge: SURVEY.md H1)
+        tree_rows_load(P, g, slot, rows);
+        if (!verified && !(rows.key.k0 == k0 && rows.key.k1 == k1)) slot = -1;
+      }
+      if (slot < 0) {
+        slot = tree_hash_find(P, g, k0, k1, &miss_pos);
+        dbg_probes += 1;
+        if (slot >= 0) tree_rows_load(P, g, slot, rows);
+      }
       if (slot < 0) {                                       // MCTS.py:89: leaf -> wait for the net
         if (IFX_LANE0) P.leaves[g] = st;
+        IFX_FOR_LANES(l) { if (l < depth) P.path[(int64_t)g * IFX_MAX_DEPTH + l] = path[l]; }
         tree_write_nn_input(P, G, st, nn_in + (int64_t)g * 196);
-        G.path_len = depth; G.pending = 1;
+        G.path_len = depth; G.pending = 1; G.leaf_hpos = miss_pos;
         break;
       }
       G.n_visits += 1;
-      const int a = tree_select(P, g, slot, st);
+      uint32_t raw = 0; float qsel = 0.0f;
+      const int a = tree_select(P, rows, &raw, &qsel);
       if (a < 0) { G.faults |= IFX_F_NOVALID; break; }
       if (depth >= P.maxd) { G.faults |= IFX_F_DEPTH; break; }
-      if (IFX_LANE0) path[depth] = ((uint32_t)slot << 9) | (uint32_t)a;
+      IFX_FOR_LANES(l) {
+        if (l == depth) {
+          IfxU4 e; e.x = ((uint32_t)slot << 9) | (uint32_t)a; e.y = raw; e.z = ifx_f2u(qsel); e.w = (uint32_t)rows.head.ns;
+          path[l] = e;
+        }
+      }
       depth += 1;
+      dbg_depth = depth > dbg_depth ? depth : dbg_depth;
       ifx_apply(st, a);                                     // MCTS.py:132
+      const uint32_t hint = (raw >> IFX_N_HINT_SHIFT) & IFX_N_HINT_NONE;
+      slot = (hint != IFX_N_HINT_NONE && (int)hint < P.C) ? (int)hint : -1;
+      verified = false;
     }
     if (G.pending) break;
   }
   if (IFX_LANE0) P.games[g] = G;
+  if (P.debug && IFX_LANE0) {
+    uint64_t* d = P.debug + (int64_t)g * 4;
+    d[0] = dbg_t0; d[1] = ifx_now_ns(); d[2] = (uint64_t)dbg_depth; d[3] = (uint64_t)dbg_probes;
+  }
 }
+
+#ifdef IFX_HOSTSIM
+static inline uint64_t ifx_cas64(uint64_t* p, uint64_t expect, uint64_t desired) {
+  const uint64_t old = *p; if (old == expect) *p = desired; return old;
+}
+#else
+IFX_D uint64_t ifx_cas64(uint64_t* p, uint64_t expect, uint64_t desired) {
+  return (uint64_t)atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)expect,
+                             (unsigned long long)desired);
+}
+#endif
 
 // ---- start of a move: reclaim nodes the new root can no longer reach, rebuild hash + free stack ----
 // A node is reachable only if its turn plane exceeds the root's (the key contains the turn), or it is the
-// root itself.
+// root itself.  Survivors are re-inserted 32 at a time (one per lane, claimed by CAS).
 IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
   IfxGame G = P.games[g];
   const ifx_state root = P.roots[g];
@@ -322,65 +506,72 @@ IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
   IFX_SYNCWARP();
   const uint64_t r0 = ifx_key0(root), r1 = ifx_key1(root);
   const int rturn = (int)root.turn;
-  int free_top = 0, live = 0;
+  int free_top = 0, live = 0, root_slot = -1;
   for (int base = 0; base < P.C; base += 32) {
-    LaneVar<int> is_live, is_free;
-    LaneVar<uint64_t> k0v, k1v;
+    LaneVar<int> is_live, is_free, is_root;
     IFX_FOR_LANES(l) {
       const int s = base + l;
-      int lv = 0, fr = 0;
+      int lv = 0, fr = 0, rt = 0;
       uint64_t k0 = IFX_KEY_EMPTY, k1 = 0;
       if (s < P.C) {
         if (!clear_all) { const IfxKey k = keys[s]; k0 = k.k0; k1 = k.k1; }
         if (k0 != IFX_KEY_EMPTY) {
-          const int t = ifx_key_turn(k0);
-          lv = (t > rturn || (k0 == r0 && k1 == r1)) ? 1 : 0;
+          rt = (k0 == r0 && k1 == r1) ? 1 : 0;
+          lv = (ifx_key_turn(k0) > rturn || rt) ? 1 : 0;
         }
         fr = !lv;
         if (fr && (clear_all || k0 != IFX_KEY_EMPTY)) { IfxKey e; e.k0 = IFX_KEY_EMPTY; e.k1 = 0; keys[s] = e; }
+        if (lv) {                                           // claim the first empty entry of the probe sequence
+          uint32_t idx = ifx_hash_key(k0, k1) & (uint32_t)(P.H - 1);
+          for (int tries = 0; tries < P.H; ++tries) {
+            if (ifx_cas64(&tab[idx].k0, IFX_KEY_EMPTY, k0) == IFX_KEY_EMPTY) {
+              tab[idx].k1 = k1 | ((uint64_t)s << 50);
+              break;
+            }
+            idx = (idx + 1) & (uint32_t)(P.H - 1);
+          }
+        }
       }
-      is_live[l] = lv; is_free[l] = fr; k0v[l] = k0; k1v[l] = k1;
+      is_live[l] = lv; is_free[l] = fr; is_root[l] = rt;
     }
-    const uint32_t mf = lanes_ballot(is_free);
-    uint32_t ml = lanes_ballot(is_live);
+    const uint32_t mf = lanes_ballot(is_free), ml = lanes_ballot(is_live), mr = lanes_ballot(is_root);
     IFX_FOR_LANES(l) {
       if (is_free[l]) fs[free_top + ifx_popc32(mf & ((1u << l) - 1u))] = (uint16_t)(base + l);
     }
     free_top += ifx_popc32(mf);
     live += ifx_popc32(ml);
-    while (ml) {                                            // re-insert the survivors
-      const int l = ifx_ffs32(ml) - 1;
-      ml &= ml - 1;
-      tree_hash_insert(P, g, lanes_bcast(k0v, l), lanes_bcast(k1v, l), base + l);
-    }
+    if (mr) root_slot = base + ifx_ffs32(mr) - 1;
   }
+  IFX_SYNCWARP();
+  // pop the slot of the next expansion ahead of time
+  G.next_slot = -1;
+  if (free_top > 0) { G.next_slot = (int)fs[free_top - 1]; free_top -= 1; }
   G.free_top = free_top;
   G.n_live = live;
+  G.root_slot = root_slot;
   G.pending = 0;
   G.path_len = 0;
+  G.leaf_hpos = -1;
   G.sims_done = root.outcome == IFX_ONGOING ? 0 : P.num_sims;   // a finished game is never searched
   if (IFX_LANE0) P.games[g] = G;
 }
 
 // ---- root statistics / action choice -----------------------------------------------------------
-IFX_D int tree_root_slot(const TreeParams& P, int g) {
-  const ifx_state root = P.roots[g];
-  return tree_hash_find(P, g, ifx_key0(root), ifx_key1(root));
-}
+IFX_D int tree_root_slot(const TreeParams& P, int g) { return P.games[g].root_slot; }
 
 // Action of Coach.py:66-81: temp = int(move+1 < temp_threshold); buf holds >= 352 ints of scratch.
 IFX_D int tree_sample_action(const TreeParams& P, int g, int temp_threshold, int* buf) {
   const IfxGame G = P.games[g];
   const ifx_state root = P.roots[g];
   if (root.outcome != IFX_ONGOING || G.faults) return -1;
-  const int slot = tree_root_slot(P, g);
+  const int slot = G.root_slot;
   if (slot < 0) return -1;
   const uint32_t* nrow = reinterpret_cast<const uint32_t*>(tree_row(P, g, slot, 1));
   LaneVar<int> lmax, lsum;
   IFX_FOR_LANES(l) {
     int mx = 0, sm = 0;
     for (int a = l; a < IFX_ROW; a += 32) {
-      const int c = a < IFX_ACTIONS ? (int)(nrow[a] & ~IFX_N_TAG) : 0;
+      const int c = a < IFX_ACTIONS ? (int)ifx_n_count(nrow[a]) : 0;
       buf[a] = c; mx = c > mx ? c : mx; sm += c;
     }
     lmax[l] = mx; lsum[l] = sm;

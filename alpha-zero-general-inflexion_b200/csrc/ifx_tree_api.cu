@@ -14,10 +14,10 @@ static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 static int check_cfg(const ifx_mcts_config* c) {
   if (!c) return IFX_E_ARG;
-  if (c->n_games <= 0 || c->nodes_per_game < 32 || c->nodes_per_game > 16384) return IFX_E_ARG;
+  if (c->n_games <= 0 || c->nodes_per_game < 32 || c->nodes_per_game > 16383) return IFX_E_ARG;
   if (c->hash_per_game < 64 || (c->hash_per_game & (c->hash_per_game - 1))) return IFX_E_ARG;
   if (c->hash_per_game < 2 * c->nodes_per_game) return IFX_E_ARG;
-  if (c->max_depth < 1 || c->max_depth > 512 || c->num_sims < 0) return IFX_E_ARG;
+  if (c->max_depth < 1 || c->max_depth > IFX_MAX_DEPTH || c->num_sims < 0) return IFX_E_ARG;
   if (c->policy_is_logits != 0) return IFX_E_ARG;          // softmax is left to the net in this version
   return IFX_OK;
 }
@@ -64,8 +64,8 @@ IFX_D void body_root_stats(const TreeParams& P, int g, int32_t* counts, float* q
   IFX_FOR_LANES(l) {
     for (int a = l; a < IFX_ACTIONS; a += 32) {
       const uint32_t raw = nrow ? nrow[a] : 0u;
-      const uint32_t n = raw & ~IFX_N_TAG;
-      const bool is64 = (raw & IFX_N_TAG) != 0;
+      const uint32_t n = ifx_n_count(raw);
+      const bool is64 = raw != IFX_N_INVALID && (raw & IFX_N_TAG) != 0;
       const int64_t o = (int64_t)g * IFX_ACTIONS + a;
       if (counts) counts[o] = (int32_t)n;
       if (q32) q32[o] = n ? qrow[a] : 0.0f;
@@ -73,7 +73,7 @@ IFX_D void body_root_stats(const TreeParams& P, int g, int32_t* counts, float* q
       if (qkind) qkind[o] = (uint8_t)(n && !is64);
     }
   }
-  if (ns && IFX_LANE0) ns[g] = slot >= 0 ? P.node_ns[(int64_t)g * P.C + slot] : 0;
+  if (ns && IFX_LANE0) ns[g] = slot >= 0 ? P.node_head[(int64_t)g * P.C + slot].ns : 0;
 }
 
 IFX_D void body_status(const TreeParams& P, int g, int32_t* status) {
@@ -87,8 +87,11 @@ IFX_D void body_status(const TreeParams& P, int g, int32_t* status) {
 #ifndef IFX_HOSTSIM
 #define TREE_WARPS 4
 #define TREE_BLOCK (TREE_WARPS * 32)
+#ifndef IFX_WAVE_MIN_BLOCKS
+#define IFX_WAVE_MIN_BLOCKS 5      // resident CTAs per SM the wave kernel is compiled for (register cap 65536/(128*n))
+#endif
 
-__global__ void __launch_bounds__(TREE_BLOCK)
+__global__ void __launch_bounds__(TREE_BLOCK, IFX_WAVE_MIN_BLOCKS)
 tree_wave_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_stride, const float* __restrict__ nn_v,
                  float* __restrict__ nn_in) {
   __shared__ float buf[TREE_WARPS][IFX_ROW];
@@ -161,11 +164,11 @@ int ifx_mcts_get_layout(const ifx_mcts_config* c, ifx_mcts_layout* L) {
   L->rows = off;       off = align256(off + G * C * 3 * IFX_ROW * 4);
   L->q64 = off;        off = align256(off + G * C * 344 * 8);
   L->node_key = off;   off = align256(off + G * C * 16);
-  L->node_ns = off;    off = align256(off + G * C * 4);
+  L->node_head = off;  off = align256(off + G * C * 16);
   L->hash = off;       off = align256(off + G * H * 16);
   L->free_stack = off; off = align256(off + G * C * 2);
   L->per_game = off;   off = align256(off + G * (int64_t)sizeof(IfxGame));
-  L->path = off;       off = align256(off + G * c->max_depth * 4);
+  L->path = off;       off = align256(off + G * IFX_MAX_DEPTH * 16);
   L->roots = off;      off = align256(off + G * (int64_t)sizeof(ifx_state));
   L->leaves = off;     off = align256(off + G * (int64_t)sizeof(ifx_state));
   L->total = off;
@@ -187,11 +190,12 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   char* b = (char*)ws;
   TreeParams& P = m->P;
   P.rows = (float*)(b + L.rows); P.q64 = (double*)(b + L.q64); P.node_key = (IfxKey*)(b + L.node_key);
-  P.node_ns = (int32_t*)(b + L.node_ns); P.hash = (IfxKey*)(b + L.hash);
+  P.node_head = (IfxHead*)(b + L.node_head); P.hash = (IfxKey*)(b + L.hash);
   P.free_stack = (uint16_t*)(b + L.free_stack); P.games = (IfxGame*)(b + L.per_game);
-  P.path = (uint32_t*)(b + L.path); P.roots = (ifx_state*)(b + L.roots); P.leaves = (ifx_state*)(b + L.leaves);
+  P.path = (IfxU4*)(b + L.path); P.roots = (ifx_state*)(b + L.roots); P.leaves = (ifx_state*)(b + L.leaves);
   P.G = c->n_games; P.C = c->nodes_per_game; P.H = c->hash_per_game; P.maxd = c->max_depth;
   P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.cpuct = c->cpuct; P.seed = c->seed;
+  P.debug = nullptr;
   *out = m;
   return IFX_OK;
 }
@@ -202,6 +206,12 @@ int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct) {
   if (!m || num_sims < 0) return IFX_E_ARG;
   m->P.num_sims = m->cfg.num_sims = num_sims;
   m->P.cpuct = m->cfg.cpuct = cpuct;
+  return IFX_OK;
+}
+
+int ifx_mcts_set_debug(ifx_mcts* m, uint64_t* buf) {
+  if (!m) return IFX_E_ARG;
+  m->P.debug = buf;
   return IFX_OK;
 }
 

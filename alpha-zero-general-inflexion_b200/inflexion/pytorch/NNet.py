@@ -27,7 +27,7 @@ args = dotdict({
 
 
 class NNetWrapper(NeuralNet):
-    def __init__(self, game, device=None, infer_dtype=torch.bfloat16):
+    def __init__(self, game, device=None, infer_dtype=torch.float16):
         self.nnet = InflexionNNet(game, args)
         self.depth, self.board_x, self.board_y = 4, *game.board_shape
         self.action_size = game.max_actions
@@ -94,7 +94,8 @@ class NNetWrapper(NeuralNet):
         return torch.exp(log_pi).cpu().numpy()[0], v.cpu().numpy()[0]
 
     def predict_batch(self, planes: torch.Tensor):
-        """float32 [B,4,7,7] on the device -> (pi float32 [B,343], v float32 [B]).  BN-folded bf16 graph."""
+        """float32 [B,4,7,7] on the device -> (pi float32 [B,343], v float32 [B]).  BN-folded 16-bit graph
+        (fp16 by default: see FoldedInference for the measured deviation from the fp32 module)."""
         if self._folded is None:
             self.nnet.eval()
             self._folded = FoldedInference(self.nnet, self.infer_dtype)

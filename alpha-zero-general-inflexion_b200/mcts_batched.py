@@ -26,12 +26,12 @@ def default_pool_size(num_sims: int) -> int:
     n = 64
     while n < 10 * max(num_sims, 1):
         n *= 2
-    return min(n, 16384)
+    return min(n, 16383)
 
 
 class BatchedMCTS:
     def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | None = None,
-                 max_depth: int = 64, backend: Backend | None = None):
+                 max_depth: int = 32, backend: Backend | None = None):
         self.be = backend or default_backend()
         self.n_games, self.num_sims = int(n_games), int(num_sims)
         nodes = int(nodes_per_game or default_pool_size(num_sims))
@@ -56,7 +56,8 @@ class BatchedMCTS:
         g = self.n_games
         # net I/O buffers (persistent so the wave + net step can be captured in a CUDA graph)
         self.nn_in = self.be.zeros((g, 4, 7, 7), torch.float32)
-        self.nn_pi = self.be.zeros((g, 343), torch.float32)
+        self._nn_pi_rows = self.be.zeros((g, 352), torch.float32)    # rows padded to 352 floats: 16-byte aligned
+        self.nn_pi = self._nn_pi_rows[:, :343]
         self.nn_v = self.be.zeros((g,), torch.float32)
         self.waves_run = 0
         self.evals_run = 0
@@ -184,5 +185,5 @@ class BatchedMCTS:
         return {
             "P": rows[:, :, 0, :343].view(np.float32), "Nraw": rows[:, :, 1, :343], "Q32": rows[:, :, 2, :343].view(np.float32),
             "Q64": view(L.q64, np.float64, (g, n, 344))[:, :, :343],
-            "key": view(L.node_key, np.uint64, (g, n, 2)), "ns": view(L.node_ns, np.int32, (g, n)),
+            "key": view(L.node_key, np.uint64, (g, n, 2)), "ns": view(L.node_head, np.int32, (g, n, 4))[:, :, 0],
         }

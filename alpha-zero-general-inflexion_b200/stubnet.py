@@ -28,6 +28,15 @@ def _coef(device):
     return _COEF[key]
 
 
+def _divisor(device):
+    """float32(1000003) as a DEVICE tensor: dividing by a Python scalar lets torch's CUDA kernel multiply by the
+    reciprocal instead, which rounds differently from the CPU's true division."""
+    key = "div:" + str(device)
+    if key not in _COEF:
+        _COEF[key] = torch.tensor(1000003.0, dtype=torch.float32).to(device)
+    return _COEF[key]
+
+
 def _mix(h):
     h = (h ^ (h >> 15)) & _MASK31
     h = (h * 0x2C1B3C6D) & _MASK31
@@ -49,7 +58,7 @@ def stub_policy_value(planes: torch.Tensor, mode: str = "float"):
     else:
         # a few large priors make the trees several plies deep, like a trained net's would
         peaked = torch.where((z >> 8) % 11 == 0, sharp * 64, sharp)
-        pi = peaked.to(torch.float32) / 1000003.0        # float32 / float32(1000003): one IEEE division
+        pi = peaked.to(torch.float32) / _divisor(x.device)                # one IEEE float32 division per element
     hv = _mix(h ^ 0x5BD1E995)
     v = ((hv & 0xFFFF) - 32768).to(torch.float32) / 32768.0               # dyadic in [-1, 1)
     return pi, v

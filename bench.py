@@ -323,7 +323,7 @@ def run_ours(a):
         line = {
             "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 tree arithmetic (bit-exact numpy semantics); bf16 net" if a.net == "default" else "f32",
+            "vs_baseline": None, "dtype": "f32 tree arithmetic (bit-exact numpy semantics); fp16 net, fp32 accumulate" if a.net == "default" else "f32",
             "data": "synthetic", "games_per_s": value / (a.sims * MOVES_PER_GAME),
             "config": workload_config(a, a.games),
             "roofline": {"kernel": "tree_wave_kernel", "bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -332,7 +332,7 @@ def run_ours(a):
                          "launches": n_tree, "share_of_step": tree_ms / elapsed_ms,
                          "visits_per_sim": visits / max(sims_rank, 1), "expansions_per_sim": expansions / max(sims_rank, 1)},
             "roofline_net": None if net_tflops is None else {
-                "kernel": "policy-value net forward (cuDNN/cuBLAS bf16, library)", "bound": "tensor", "achieved": net_tflops,
+                "kernel": "policy-value net forward (cuDNN/cuBLAS fp16, library)", "bound": "tensor", "achieved": net_tflops,
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": net_tflops / tensor_peak, "share_of_step": net_ms / elapsed_ms},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }

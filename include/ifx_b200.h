@@ -118,9 +118,9 @@ IFX_API int ifx_rules_info_host(const ifx_state* states, int64_t n, int32_t* inf
 
 typedef struct ifx_mcts_config {
   int32_t n_games;          /* concurrent game trees on this GPU                                  */
-  int32_t nodes_per_game;   /* node pool capacity per game (<= 16384)                             */
+  int32_t nodes_per_game;   /* node pool capacity per game (<= 16383)                             */
   int32_t hash_per_game;    /* hash slots per game, power of two, >= 2*nodes_per_game             */
-  int32_t max_depth;        /* longest search path kept (<= 512)                                  */
+  int32_t max_depth;        /* longest search path kept (<= 32: one level per lane)               */
   int32_t num_sims;         /* args.numMCTSSims (MCTS.py:45)                                      */
   float cpuct;              /* float32(args.cpuct) (MCTS.py:122; NEP-50 weak scalar)              */
   uint64_t seed;            /* Philox key for every random draw on the path    */
@@ -134,14 +134,14 @@ typedef struct ifx_mcts ifx_mcts;
 /* Offsets (bytes) of the SoA pools inside the workspace, for inspection by tests (MCTS tables
  * Qsa/Nsa/Ns/Ps of MCTS.py:25-31 are not read by any caller of the reference). */
 typedef struct ifx_mcts_layout {
-  int64_t rows;       /* float [G][C][3][352]: P, N (int32, bit31 = Q is a Python-float), Q (float32)  */
+  int64_t rows;       /* float [G][C][3][352]: P, N word (count | child hint | kind; see ifx_tree.cuh), Q */
   int64_t q64;        /* double [G][C][344]: Q when its kind is Python-float       */
   int64_t node_key;   /* uint64 [G][C][2]                                                               */
-  int64_t node_ns;    /* int32 [G][C]                                                                   */
+  int64_t node_head;  /* {int32 Ns, float sqrt(Ns), float sqrt(Ns+1e-8), pad} [G][C]                    */
   int64_t hash;       /* uint64 [G][H][2]                                                               */
   int64_t free_stack; /* uint16 [G][C]                                                                  */
   int64_t per_game;   /* struct per game, see csrc/ifx_tree.cuh                                         */
-  int64_t path;       /* uint32 [G][max_depth]                                                          */
+  int64_t path;       /* uint32x4 [G][32]: {slot<<9|action, N word, Q bits, Ns} per path level           */
   int64_t roots;      /* ifx_state [G]                                                                  */
   int64_t leaves;     /* ifx_state [G]                                                                  */
   int64_t total;      /* == ifx_mcts_workspace_bytes                                                    */
@@ -154,6 +154,9 @@ IFX_API size_t ifx_mcts_workspace_bytes(const ifx_mcts_config* cfg);
 IFX_API int ifx_mcts_create(const ifx_mcts_config* cfg, void* workspace, size_t workspace_bytes, ifx_mcts** out);
 IFX_API void ifx_mcts_destroy(ifx_mcts* m);
 IFX_API int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct);
+/* Optional per-game timing trace of ifx_mcts_wave: buf = device uint64 [G][4] receiving {start ns, end ns
+ * (%globaltimer), deepest level reached, hash probes}; NULL switches it off (the default). */
+IFX_API int ifx_mcts_set_debug(ifx_mcts* m, uint64_t* buf);
 
 /* Empty trees + install roots (MCTS.reset, MCTS.py:147-148, followed by the first getActionProb).
  * roots[g].tag is the game id used as the RNG stream coordinate.  `which` (nullable, int32 [G]) selects

@@ -117,11 +117,13 @@ def test_full_tables_match_oracle(backend):
             assert tv["P"][0, slot].tobytes() == orc.P[key].astype(np.float32).tobytes()
             assert tv["ns"][0, slot] == orc.Ns[key]
             for a in range(343):
-                n = int(tv["Nraw"][0, slot, a]) & 0x7FFFFFFF
+                raw = int(tv["Nraw"][0, slot, a])
+                n = 0 if raw == 0xFFFFFFFF else raw & 0x1FFFF
+                assert (raw == 0xFFFFFFFF) == (orc.V[key][a] == 0)
                 assert n == orc.N.get((key, a), 0)
                 if n:
                     q = orc.Q[(key, a)]
-                    is64 = bool(int(tv["Nraw"][0, slot, a]) >> 31)
+                    is64 = bool(raw >> 31)
                     assert is64 == (not q.is32)
                     got = tv["Q64"][0, slot, a] if is64 else np.float64(tv["Q32"][0, slot, a])
                     assert np.float64(got).tobytes() == np.float64(q.x).tobytes()
