@@ -49,6 +49,8 @@ PROTOTYPES = {
     "ifx_mcts_create": (c_int, [C.POINTER(MctsConfig), c_void_p, c_size_t, C.POINTER(c_void_p)]),
     "ifx_mcts_destroy": (None, [c_void_p]),
     "ifx_mcts_set_params": (c_int, [c_void_p, c_int32, c_float]),
+    "ifx_mcts_wave_timing": (c_int, [c_void_p, c_int]),
+    "ifx_mcts_wave_time": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int32)]),
     "ifx_mcts_set_debug": (c_int, [c_void_p, c_void_p]),
     "ifx_mcts_reset_games": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_set_roots": (c_int, [c_void_p, c_void_p, c_void_p]),

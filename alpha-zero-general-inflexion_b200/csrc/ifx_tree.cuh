@@ -74,7 +74,7 @@ struct TreeParams {
   ifx_state* roots;     // [G]
   ifx_state* leaves;    // [G]
   int32_t G, C, H, maxd, num_sims, logits;
-  uint64_t* debug;      // optional [G][4]: wave start / end (globaltimer ns), deepest level, hash probes
+  uint64_t* debug;      // optional [G][8]: ns stamps {start, loads done, expanded, backed up, first level done, end}, depth, probes
   float cpuct;
   uint64_t seed;
 };
@@ -220,12 +220,15 @@ IFX_D int tree_select(const TreeParams& P, const RowRegs& R, uint32_t* chosen_ra
     float best = -INFINITY, qsel = 0.0f; int arg = 0x7fffffff; uint32_t raw = 0;
     // ascending action order inside the lane, strict '>' keeps the lowest index on ties
 #define IFX_PUCT(PV, NV, QV, A)                                                                       \
-    do { if ((NV) != IFX_N_INVALID) {                                                                 \
-        const float cp = ifx_fmul(P.cpuct, (PV));                                                     \
-        const uint32_t n_ = (NV) & IFX_N_COUNT;                                                       \
-        const float u = n_ ? ifx_fadd((QV), ifx_fdiv(ifx_fmul(cp, sq_seen), (float)(1u + n_)))        \
-                           : ifx_fmul(cp, sq_unseen);                                                 \
-        if (u > best) { best = u; arg = (A); raw = (NV); qsel = (QV); } } } while (0)
+    do { /* straight-line (no divergent branches) so the twelve independent chains of a lane interleave */ \
+      const bool ok_ = (NV) != IFX_N_INVALID;                                                         \
+      const uint32_t n_ = (NV) & IFX_N_COUNT;                                                         \
+      const bool seen_ = ok_ && n_ != 0u;                                                             \
+      const float cp = ifx_fmul(P.cpuct, (PV));                                                       \
+      /* a dummy numerator for edges that do not use the quotient keeps 0/x out of the division's slow path */ \
+      const float quo = ifx_fdiv(seen_ ? ifx_fmul(cp, sq_seen) : 1.0f, (float)(1u + n_));             \
+      const float u = seen_ ? ifx_fadd((QV), quo) : ifx_fmul(cp, sq_unseen);                          \
+      if (ok_ && u > best) { best = u; arg = (A); raw = (NV); qsel = (QV); } } while (0)
 #define IFX_PUCT4(PV, NV, QV, BASE)                                                                   \
     IFX_PUCT(PV.x, NV.x, QV.x, (BASE)); IFX_PUCT(PV.y, NV.y, QV.y, (BASE) + 1);                       \
     IFX_PUCT(PV.z, NV.z, QV.z, (BASE) + 2); IFX_PUCT(PV.w, NV.w, QV.w, (BASE) + 3)
@@ -338,8 +341,11 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
           v.x = (b & 1u) ? 1.0f : 0.0f; v.y = (b & 2u) ? 1.0f : 0.0f;
           v.z = (b & 4u) ? 1.0f : 0.0f; v.w = (b & 8u) ? 1.0f : 0.0f;
         }
-        v.x = ifx_fdiv(v.x, total); v.y = ifx_fdiv(v.y, total);         // policies /= sum
-        v.z = ifx_fdiv(v.z, total); v.w = ifx_fdiv(v.w, total);
+        // policies /= sum.  Invalid entries are exactly 0 either way; dividing a dummy 1.0 for them keeps the
+        // zero numerators out of the IEEE division's slow path (which the whole warp would otherwise take).
+        const float qx = ifx_fdiv((b & 1u) ? v.x : 1.0f, total), qy = ifx_fdiv((b & 2u) ? v.y : 1.0f, total);
+        const float qz = ifx_fdiv((b & 4u) ? v.z : 1.0f, total), qw = ifx_fdiv((b & 8u) ? v.w : 1.0f, total);
+        v.x = (b & 1u) ? qx : 0.0f; v.y = (b & 2u) ? qy : 0.0f; v.z = (b & 4u) ? qz : 0.0f; v.w = (b & 8u) ? qw : 0.0f;
         *reinterpret_cast<IfxF4*>(prow + i) = v;
         IfxU4 z;                                             // Vs[s] folded into the N row (MCTS.py:109)
         z.x = (b & 1u) ? IFX_N_FRESH : IFX_N_INVALID; z.y = (b & 2u) ? IFX_N_FRESH : IFX_N_INVALID;
@@ -391,6 +397,7 @@ IFX_D uint64_t ifx_now_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltime
 IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_t pi_stride, const float* nn_v,
                           float* nn_in, float* buf) {
   const uint64_t dbg_t0 = P.debug ? ifx_now_ns() : 0;
+  uint64_t dbg_t1 = 0, dbg_t2 = 0, dbg_t3 = 0, dbg_t4 = 0;
   int dbg_depth = 0, dbg_probes = 0;
   // round trip 1: everything whose address is known up front, issued together (leaf / policy / value are
   // speculative: they are only used when a leaf is pending, which is the common case)
@@ -403,8 +410,10 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   LaneVar<IfxU4> path;
   IFX_FOR_LANES(l) { path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
   if (G.faults) return;
+  if (P.debug) dbg_t1 = ifx_now_ns() + (uint64_t)(G.pending & 0) + (uint64_t)(leaf.turn & 0);
   if (G.pending) {
     const int slot = tree_expand(P, g, G, leaf, pol, buf);
+    if (P.debug) dbg_t2 = ifx_now_ns();
     if (slot >= 0) {
       if (G.path_len == 0) G.root_slot = slot;              // the root itself was the leaf
       // search() of the leaf returns -v, v a float32 (MCTS.py:112; NNet.py:94)
@@ -412,6 +421,7 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
       G.sims_done += 1; G.n_sims += 1;
     }
     G.pending = 0;
+    if (P.debug) dbg_t3 = ifx_now_ns();
   }
   while (!G.faults && G.sims_done < P.num_sims) {
     ifx_state st = P.roots[g];
@@ -457,6 +467,7 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
         }
       }
       depth += 1;
+      if (P.debug && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
       dbg_depth = depth > dbg_depth ? depth : dbg_depth;
       ifx_apply(st, a);                                     // MCTS.py:132
       const uint32_t hint = (raw >> IFX_N_HINT_SHIFT) & IFX_N_HINT_NONE;
@@ -467,8 +478,9 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   }
   if (IFX_LANE0) P.games[g] = G;
   if (P.debug && IFX_LANE0) {
-    uint64_t* d = P.debug + (int64_t)g * 4;
-    d[0] = dbg_t0; d[1] = ifx_now_ns(); d[2] = (uint64_t)dbg_depth; d[3] = (uint64_t)dbg_probes;
+    uint64_t* d = P.debug + (int64_t)g * 8;
+    d[0] = dbg_t0; d[1] = dbg_t1; d[2] = dbg_t2; d[3] = dbg_t3; d[4] = dbg_t4; d[5] = ifx_now_ns();
+    d[6] = (uint64_t)dbg_depth; d[7] = (uint64_t)dbg_probes;
   }
 }
 

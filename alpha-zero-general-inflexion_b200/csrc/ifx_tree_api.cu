@@ -3,11 +3,20 @@
 #include "ifx_host.cuh"
 #include <new>
 
+#define IFX_TIMING_RING 4096
 struct ifx_mcts {
   ifx_mcts_config cfg;
   ifx_mcts_layout lay;
   TreeParams P;
   void* workspace;
+  // optional CUDA-event timing of the wave kernel (bench evidence): a ring of event pairs recorded right around
+  // the launch on the launching stream, summed by ifx_mcts_wave_time
+  bool timing = false;
+  int n_timed = 0;
+#ifndef IFX_HOSTSIM
+  cudaEvent_t ev[IFX_TIMING_RING][2];
+  int ev_made = 0;
+#endif
 };
 
 static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
@@ -200,7 +209,36 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   return IFX_OK;
 }
 
-void ifx_mcts_destroy(ifx_mcts* m) { delete m; }
+void ifx_mcts_destroy(ifx_mcts* m) {
+  if (!m) return;
+#ifndef IFX_HOSTSIM
+  for (int i = 0; i < m->ev_made; ++i) { cudaEventDestroy(m->ev[i][0]); cudaEventDestroy(m->ev[i][1]); }
+#endif
+  delete m;
+}
+
+int ifx_mcts_wave_timing(ifx_mcts* m, int enable) {
+  if (!m) return IFX_E_ARG;
+  m->timing = enable != 0;
+  m->n_timed = 0;
+  return IFX_OK;
+}
+
+int ifx_mcts_wave_time(ifx_mcts* m, double* total_ms, int32_t* launches) {
+  if (!m || !total_ms || !launches) return IFX_E_ARG;
+  double sum = 0.0;
+#ifndef IFX_HOSTSIM
+  for (int i = 0; i < m->n_timed; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(m->ev[i][1]) || cudaEventElapsedTime(&ms, m->ev[i][0], m->ev[i][1]))
+      return ifx_set_cuda_error((int)cudaGetLastError());
+    sum += ms;
+  }
+#endif
+  *total_ms = sum; *launches = m->n_timed;
+  m->n_timed = 0;
+  return IFX_OK;
+}
 
 int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct) {
   if (!m || num_sims < 0) return IFX_E_ARG;
@@ -244,7 +282,16 @@ int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const floa
   for (int g = 0; g < m->P.G; ++g) tree_wave_game(m->P, g, nn_pi, pi_stride, nn_v, nn_in, buf);
   return ifx_after_launch();
 #else
+  const bool timed = m->timing && m->n_timed < IFX_TIMING_RING;
+  if (timed) {
+    while (m->ev_made <= m->n_timed) {
+      if (cudaEventCreate(&m->ev[m->ev_made][0]) || cudaEventCreate(&m->ev[m->ev_made][1])) return ifx_set_cuda_error((int)cudaGetLastError());
+      m->ev_made += 1;
+    }
+    cudaEventRecord(m->ev[m->n_timed][0], (cudaStream_t)stream);
+  }
   tree_wave_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
+  if (timed) { cudaEventRecord(m->ev[m->n_timed][1], (cudaStream_t)stream); m->n_timed += 1; }
   return ifx_after_launch();
 #endif
 }

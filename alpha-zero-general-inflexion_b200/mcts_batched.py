@@ -124,6 +124,16 @@ class BatchedMCTS:
                 self.nn_v.copy_(v.reshape(-1))
             self.evals_run += 1
 
+    def wave_timing(self, enable: bool) -> None:
+        """Bracket every (un-captured) wave launch with CUDA events inside the library call (see ifx_mcts_wave_timing)."""
+        self.be.check(self.be.dll.ifx_mcts_wave_timing(self._h, 1 if enable else 0))
+
+    def wave_time(self):
+        """-> (summed wave-kernel milliseconds, launches) since the last read-out; synchronises on the events."""
+        ms, n = C.c_double(0.0), C.c_int32(0)
+        self.be.check(self.be.dll.ifx_mcts_wave_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # ---- results --------------------------------------------------------------------------------
     def root_stats(self, want_q: bool = False) -> dict:
         g = self.n_games

@@ -75,8 +75,11 @@ class SelfPlayEngine:
             self._wave_and_net()
 
     def search(self, wave_timer=None) -> None:
-        """The numMCTSSims loop for all games.  ``wave_timer(fn)`` (optional) wraps each tree-kernel launch, e.g.
-        to bracket it with CUDA events; it forces the un-captured path for the wave."""
+        """The numMCTSSims loop for all games.  ``wave_timer`` (optional): True launches every tree wave outside the
+        CUDA graph (so the library can bracket it with events, see BatchedMCTS.wave_timing); a callable wraps each
+        launch instead."""
+        if wave_timer is True:
+            wave_timer = lambda fn: fn()  # noqa: E731
         if self.use_graph and wave_timer is None:
             if self._graph is None:
                 self._capture()

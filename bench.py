@@ -246,18 +246,10 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         eng.play_move()
     eng.mcts.raise_on_faults()
-    # per-wave event timing path (un-captured wave) warm-up
-    ev_pairs = []
-
-    def timed_wave(fn):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        fn()
-        e.record()
-        ev_pairs.append((s, e))
-    eng.play_move(timed_wave)
-    ev_pairs.clear()
-
+    # per-wave event timing path (wave launched outside the graph, bracketed by events inside the library call)
+    eng.mcts.wave_timing(True)
+    eng.play_move(True)
+    eng.mcts.wave_time()
     # ---- timed region: K steps, device-resident ---------------------------------------------------------
     c0 = eng.mcts.counters()
     l0 = eng.my_launches
@@ -265,17 +257,21 @@ def run_ours(a):
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         t_start.record()
-        for _ in range(a.steps):
-            eng.play_move(timed_wave)
+        tree_ms, n_tree = 0.0, 0
+        for k in range(a.steps):
+            eng.play_move(True)
+            if (k + 1) % 30 == 0:                          # drain the library's event ring (4096 pairs) before it fills
+                ms, n = eng.mcts.wave_time()
+                tree_ms, n_tree = tree_ms + ms, n_tree + n
         t_end.record()
         barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
     c1 = eng.mcts.counters()
     eng.mcts.raise_on_faults()
     launches = eng.my_launches - l0
-    tree_ms = sum(s.elapsed_time(e) for s, e in ev_pairs)
-    n_tree = len(ev_pairs)
-    ev_pairs.clear()
+    ms, n = eng.mcts.wave_time()                           # CUDA events recorded around every wave launch
+    tree_ms, n_tree = tree_ms + ms, n_tree + n
+    eng.mcts.wave_timing(False)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=be.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

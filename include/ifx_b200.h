@@ -154,8 +154,14 @@ IFX_API size_t ifx_mcts_workspace_bytes(const ifx_mcts_config* cfg);
 IFX_API int ifx_mcts_create(const ifx_mcts_config* cfg, void* workspace, size_t workspace_bytes, ifx_mcts** out);
 IFX_API void ifx_mcts_destroy(ifx_mcts* m);
 IFX_API int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct);
-/* Optional per-game timing trace of ifx_mcts_wave: buf = device uint64 [G][4] receiving {start ns, end ns
- * (%globaltimer), deepest level reached, hash probes}; NULL switches it off (the default). */
+/* CUDA-event timing of the wave kernel on its launching stream: while enabled, every ifx_mcts_wave (outside
+ * graph capture) is bracketed by an event pair recorded inside the call; ifx_mcts_wave_time synchronises on them,
+ * returns the summed kernel time and the number of launches (at most 4096 per read-out), and clears the ring. */
+IFX_API int ifx_mcts_wave_timing(ifx_mcts* m, int enable);
+IFX_API int ifx_mcts_wave_time(ifx_mcts* m, double* total_ms, int32_t* launches);
+/* Optional per-game timing trace of ifx_mcts_wave: buf = device uint64 [G][8] receiving %globaltimer stamps
+ * {start, first loads done, leaf expanded, value backed up, first tree level done, end}, the deepest level
+ * reached and the number of hash probes; NULL switches it off (the default). */
 IFX_API int ifx_mcts_set_debug(ifx_mcts* m, uint64_t* buf);
 
 /* Empty trees + install roots (MCTS.reset, MCTS.py:147-148, followed by the first getActionProb).

@@ -1,0 +1,89 @@
+"""N>1 paths on CPU with the gloo backend (world_size 2): games shard by rank with no data-path collective,
+and NNetWrapper.train averages gradients across ranks."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _selfplay_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import inflexion_b200  # noqa: F401
+    from hostsim import hostsim_backend
+    from inflexion_b200.selfplay import SelfPlayEngine
+    from inflexion_b200.stubnet import stub_policy_value
+    per_rank = 3
+    eng = SelfPlayEngine(per_rank, 10, lambda x: stub_policy_value(x), temp_threshold=3, seed=5, max_turns=5,
+                         game_id_base=rank * per_rank, backend=hostsim_backend())
+    moves = eng.play_episode()
+    acts = eng.ex_actions[:6].clone()
+    acts[moves:] = -1
+    # the only communication: gathering the (small) results, as the final example gather would
+    gathered = [torch.zeros_like(acts) for _ in range(world)]
+    dist.all_gather(gathered, acts)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sharded.npy"), torch.cat(gathered, dim=1).numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_selfplay_equals_single_process(tmp_path):
+    port = _free_port()
+    mp.spawn(_selfplay_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sharded = np.load(os.path.join(tmp_path, "sharded.npy"))
+    from hostsim import hostsim_backend
+    from inflexion_b200.selfplay import SelfPlayEngine
+    from inflexion_b200.stubnet import stub_policy_value
+    eng = SelfPlayEngine(6, 10, lambda x: stub_policy_value(x), temp_threshold=3, seed=5, max_turns=5,
+                         backend=hostsim_backend())
+    moves = eng.play_episode()
+    single = eng.ex_actions[:6].clone()
+    single[moves:] = -1
+    assert np.array_equal(sharded, single.numpy())          # game i plays the same game on whichever rank owns it
+
+
+def _train_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import inflexion_b200  # noqa: F401
+    from inflexion_b200.inflexion.pytorch import NNet as nnet_mod
+    from test_nnet import Shape, random_planes
+    nnet_mod.args.update(cuda=False, epochs=2, batch_size=16, num_channels=8)
+    torch.manual_seed(0)                                     # same initial weights on every rank
+    w = nnet_mod.NNetWrapper(Shape(), device="cpu", infer_dtype=torch.float32)
+    np.random.seed(100 + rank)                               # different batches per rank
+    planes = random_planes(48, seed=rank).astype(np.int64)
+    pis = np.full((48, 343), 1.0 / 343)
+    examples = [(planes[i], pis[i].tolist(), float((-1) ** (i + rank))) for i in range(48)]
+    w.train(examples, verbose=False)
+    flat = torch.cat([p.detach().reshape(-1) for p in w.nnet.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        torch.save(gathered, os.path.join(out_dir, "weights.pt"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_training_keeps_ranks_in_sync(tmp_path):
+    port = _free_port()
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    w0, w1 = torch.load(os.path.join(tmp_path, "weights.pt"))
+    assert torch.equal(w0, w1)                               # identical updates from all-reduced gradients
+    assert float(w0.abs().sum()) > 0
