@@ -58,6 +58,7 @@ PROTOTYPES = {
     "ifx_mcts_root_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_sample_actions": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
     "ifx_mcts_advance": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ifx_mcts_restart_finished": (c_int, [c_void_p, C.c_uint32, c_void_p, c_void_p]),
     "ifx_mcts_status": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_get_roots": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_counters": (c_int, [c_void_p, c_void_p, c_void_p]),

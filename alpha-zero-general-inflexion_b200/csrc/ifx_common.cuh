@@ -56,6 +56,30 @@ IFX_D uint32_t ifx_f2u(float f) { return __float_as_uint(f); }
 IFX_D float ifx_u2f(uint32_t u) { return __uint_as_float(u); }
 #endif
 
+// IEEE binary16 -> float32 (the net's head output in the fused-softmax mode)
+#ifdef IFX_HOSTSIM
+struct uint2 { uint32_t x, y; };
+static inline float ifx_h2f(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu;
+  uint32_t bits;
+  if (exp == 0) {
+    if (man == 0) bits = sign;
+    else { int e = -1; uint32_t m = man; do { ++e; m <<= 1; } while (!(m & 0x400u)); bits = sign | ((uint32_t)(112 - e) << 23) | ((m & 0x3FFu) << 13); }
+  } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+  else bits = sign | ((exp + 112) << 23) | (man << 13);
+  float f; memcpy(&f, &bits, 4); return f;
+}
+static inline float ifx_expf(float x) { return expf(x); }
+static inline float ifx_logf(float x) { return logf(x); }
+static inline float ifx_tanhf(float x) { return tanhf(x); }
+#else
+#include <cuda_fp16.h>
+IFX_D float ifx_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+IFX_D float ifx_expf(float x) { return expf(x); }
+IFX_D float ifx_logf(float x) { return logf(x); }
+IFX_D float ifx_tanhf(float x) { return tanhf(x); }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Per-lane variables and warp collectives.  On the device a LaneVar is one register per thread; in
 // the host simulation it is an array of 32 and the collectives loop.
@@ -95,6 +119,18 @@ static inline void lanes_bfly_fadd(LaneVar<float>& x, int mask) {
   for (int l = 0; l < 32; ++l) x[l] = t[l];
 }
 template <class T> static inline T lanes_bcast(const LaneVar<T>& x, int src) { return x[src]; }
+static inline float lanes_max_f32(const LaneVar<float>& x) {
+  float m = x[0];
+  for (int l = 1; l < 32; ++l) m = x[l] > m ? x[l] : m;
+  return m;
+}
+// butterfly sum (same association order as the device shuffles)
+static inline float lanes_sum_f32(const LaneVar<float>& x) {
+  float t[32];
+  for (int l = 0; l < 32; ++l) t[l] = x[l];
+  for (int off = 16; off > 0; off >>= 1) { float u[32]; for (int l = 0; l < 32; ++l) u[l] = t[l] + t[l ^ off]; for (int l = 0; l < 32; ++l) t[l] = u[l]; }
+  return t[0];
+}
 // out[l] = in[l + 1]  (lane 31 keeps its own value)
 static inline void lanes_shift_down(const LaneVar<uint32_t>& in, LaneVar<uint32_t>& out) {
   for (int l = 0; l < 32; ++l) out[l] = in[l < 31 ? l + 1 : 31];
@@ -114,6 +150,18 @@ IFX_D void lanes_bfly_fadd(LaneVar<float>& x, int mask) {
   x.v = __fadd_rn(x.v, __shfl_xor_sync(0xffffffffu, x.v, mask));
 }
 template <class T> IFX_D T lanes_bcast(const LaneVar<T>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
+IFX_D float lanes_max_f32(const LaneVar<float>& x) {
+  float m = x.v;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  return m;
+}
+IFX_D float lanes_sum_f32(const LaneVar<float>& x) {
+  float t = x.v;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, off));
+  return t;
+}
 IFX_D void lanes_shift_down(const LaneVar<uint32_t>& in, LaneVar<uint32_t>& out) {
   out.v = __shfl_down_sync(0xffffffffu, in.v, 1);
 }

@@ -296,6 +296,60 @@ IFX_D void tree_policy_load(const float* pi, bool aligned, PolicyRegs& R) {
   }
 }
 
+// Fused head mode (policy_is_logits = 2): `head` is the net's last GEMM output for this game, binary16
+// [>= 344]: 343 policy logits + the value pre-activation.  Computes exp(log_softmax(logits)) (NNet.py:94 with
+// InflexionNNet.py:54) and tanh(value) here, so no elementwise kernel runs between the GEMM and the tree.
+IFX_D float tree_head_softmax(const uint16_t* head, PolicyRegs& R) {
+  LaneVar<float> lmax, lsum;
+  IFX_FOR_LANES(l) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      IfxF4 v = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (i < 344) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(head + i);        // four halfs, 8-byte aligned
+        v.x = ifx_h2f((uint16_t)(raw.x & 0xFFFFu)); v.y = ifx_h2f((uint16_t)(raw.x >> 16));
+        v.z = ifx_h2f((uint16_t)(raw.y & 0xFFFFu)); v.w = ifx_h2f((uint16_t)(raw.y >> 16));
+      }
+      R.p[j][l] = v;
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), v.z));
+      if (i + 3 < IFX_ACTIONS) mx = fmaxf(mx, v.w);                         // element 343 is the value, not a logit
+    }
+    lmax[l] = mx;
+  }
+  const float m = lanes_max_f32(lmax);
+  float value = 0.0f;
+  IFX_FOR_LANES(l) {
+    float sm = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      IfxF4 v = R.p[j][l];
+      v.x = i < IFX_ACTIONS ? ifx_expf(v.x - m) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_expf(v.y - m) : 0.0f;
+      v.z = i + 2 < IFX_ACTIONS ? ifx_expf(v.z - m) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_expf(v.w - m) : 0.0f;
+      sm += (v.x + v.y) + (v.z + v.w);
+    }
+    lsum[l] = sm;
+  }
+  const float lse = ifx_logf(lanes_sum_f32(lsum));
+  LaneVar<float> val;
+  IFX_FOR_LANES(l) {
+    val[l] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      IfxF4 v = R.p[j][l];
+      if (i == 340) val[l] = ifx_tanhf(v.w);                                // lane 21, j = 2 holds element 343
+      v.x = i < IFX_ACTIONS ? ifx_expf((v.x - m) - lse) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_expf((v.y - m) - lse) : 0.0f;
+      v.z = i + 2 < IFX_ACTIONS ? ifx_expf((v.z - m) - lse) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_expf((v.w - m) - lse) : 0.0f;
+      R.p[j][l] = v;
+    }
+  }
+  value = lanes_bcast(val, 21);
+  return value;
+}
+
 // ---- expansion of the pending leaf (MCTS.py:89-112) ----
 // returns the slot, or -1 with a fault bit set
 IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, const PolicyRegs& R, float* buf) {
@@ -403,10 +457,15 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   // speculative: they are only used when a leaf is pending, which is the common case)
   IfxGame G = P.games[g];
   const ifx_state leaf = P.leaves[g];
-  const float leaf_v = nn_v[g];
+  float leaf_v;
   PolicyRegs pol;
-  const float* pi_row = nn_pi + (int64_t)g * pi_stride;
-  tree_policy_load(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, pol);
+  if (P.logits == 2) {                                      // binary16 head output: softmax + tanh fused here
+    leaf_v = tree_head_softmax(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g * pi_stride, pol);
+  } else {
+    leaf_v = nn_v[g];
+    const float* pi_row = nn_pi + (int64_t)g * pi_stride;
+    tree_policy_load(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, pol);
+  }
   LaneVar<IfxU4> path;
   IFX_FOR_LANES(l) { path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
   if (G.faults) return;

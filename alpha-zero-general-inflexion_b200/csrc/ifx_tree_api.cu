@@ -27,7 +27,7 @@ static int check_cfg(const ifx_mcts_config* c) {
   if (c->hash_per_game < 64 || (c->hash_per_game & (c->hash_per_game - 1))) return IFX_E_ARG;
   if (c->hash_per_game < 2 * c->nodes_per_game) return IFX_E_ARG;
   if (c->max_depth < 1 || c->max_depth > IFX_MAX_DEPTH || c->num_sims < 0) return IFX_E_ARG;
-  if (c->policy_is_logits != 0) return IFX_E_ARG;          // softmax is left to the net in this version
+  if (c->policy_is_logits != 0 && c->policy_is_logits != 2) return IFX_E_ARG;
   return IFX_OK;
 }
 
@@ -62,6 +62,28 @@ IFX_D void body_advance(const TreeParams& P, int g, const int32_t* actions) {
     IFX_SYNCWARP();
   }
   tree_begin_move(P, g, false);
+}
+
+// Coach.learn starts a new episode when one ends (Coach.py:108-112): finished games get the start position, an
+// empty tree and a fresh RNG stream (tag + tag_stride); `count` (nullable) accumulates how many were restarted.
+IFX_D void body_restart_finished(const TreeParams& P, int g, uint32_t tag_stride, int32_t* count) {
+  const ifx_state old = P.roots[g];
+  if (old.outcome == IFX_ONGOING) return;
+  IFX_SYNCWARP();
+  if (IFX_LANE0) {
+    ifx_state s;
+    memset(&s, 0, sizeof(s));
+    s.max_turns = old.max_turns;
+    s.tag = old.tag + tag_stride;
+    P.roots[g] = s;
+#ifdef IFX_HOSTSIM
+    if (count) *count += 1;
+#else
+    if (count) atomicAdd(count, 1);
+#endif
+  }
+  IFX_SYNCWARP();
+  tree_begin_move(P, g, true);
 }
 
 IFX_D void body_root_stats(const TreeParams& P, int g, int32_t* counts, float* q32, double* q64, uint8_t* qkind,
@@ -122,6 +144,11 @@ __global__ void __launch_bounds__(TREE_BLOCK)
 tree_advance_kernel(TreeParams P, const int32_t* __restrict__ actions) {
   const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
   if (g < P.G) body_advance(P, g, actions);
+}
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_restart_kernel(TreeParams P, uint32_t tag_stride, int32_t* count) {
+  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < P.G) body_restart_finished(P, g, tag_stride, count);
 }
 __global__ void __launch_bounds__(TREE_BLOCK)
 tree_root_stats_kernel(TreeParams P, int32_t* counts, float* q32, double* q64, uint8_t* qkind, int32_t* ns) {
@@ -276,7 +303,10 @@ int ifx_mcts_set_roots(ifx_mcts* m, const ifx_state* roots, void* stream) {
 }
 
 int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const float* nn_v, float* nn_in, void* stream) {
-  if (!m || !nn_pi || !nn_v || !nn_in || pi_stride < IFX_ACTIONS) return IFX_E_ARG;
+  if (!m || !nn_pi || !nn_in || pi_stride < IFX_ACTIONS) return IFX_E_ARG;
+  if (m->P.logits == 2) {                  // nn_pi = binary16 head rows: 343 logits + value, 8-byte aligned rows
+    if (pi_stride < 344 || (pi_stride & 3) || ((uintptr_t)nn_pi & 7)) return IFX_E_ARG;
+  } else if (!nn_v) return IFX_E_ARG;
 #ifdef IFX_HOSTSIM
   float buf[IFX_ROW];
   for (int g = 0; g < m->P.G; ++g) tree_wave_game(m->P, g, nn_pi, pi_stride, nn_v, nn_in, buf);
@@ -327,6 +357,17 @@ int ifx_mcts_advance(ifx_mcts* m, const int32_t* actions, void* stream) {
   return ifx_after_launch();
 #else
   tree_advance_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, actions);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_restart_finished(ifx_mcts* m, uint32_t tag_stride, int32_t* count, void* stream) {
+  if (!m) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  for (int g = 0; g < m->P.G; ++g) body_restart_finished(m->P, g, tag_stride, count);
+  return ifx_after_launch();
+#else
+  tree_restart_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, tag_stride, count);
   return ifx_after_launch();
 #endif
 }

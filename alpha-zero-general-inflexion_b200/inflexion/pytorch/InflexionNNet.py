@@ -96,19 +96,28 @@ class FoldedInference:
         wh = torch.cat([net.fc3.weight.detach().float(), net.fc4.weight.detach().float()], dim=0)
         bh = torch.cat([net.fc3.bias.detach().float(), net.fc4.bias.detach().float()], dim=0)
         self.head = (wh.to(dtype).contiguous(), bh.to(dtype))
+        self.head_t = self.head[0].t()
         self.n_act = net.action_size
         self.device = dev
 
-    @torch.no_grad()
-    def __call__(self, x: torch.Tensor):
+    def _trunk(self, x: torch.Tensor):
         x = x.to(self.first_dtype).contiguous(memory_format=torch.channels_last)
         s = _conv_relu(x, self.w1, self.b1, 1).to(self.dtype)
         for w, b, pad in self.convs:
             s = _conv_relu(s, w, b, pad)
         s = s.permute(0, 2, 3, 1).reshape(s.shape[0], -1)                    # NHWC flatten: a view for channels-last
         s = F.relu(F.linear(s, *self.fc1))
-        s = F.relu(F.linear(s, *self.fc2))
-        out = F.linear(s, *self.head).float()
+        return F.relu(F.linear(s, *self.fc2))
+
+    @torch.no_grad()
+    def head_into(self, x: torch.Tensor, out: torch.Tensor):
+        """Raw head output [B,344] (343 policy logits + value pre-activation) written into ``out`` by the last GEMM
+        itself; softmax / tanh are left to the consumer (the tree kernel's fused-head mode)."""
+        return torch.addmm(self.head[1], self._trunk(x), self.head_t, out=out)
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor):
+        out = F.linear(self._trunk(x), *self.head).float()
         pi = torch.exp(F.log_softmax(out[:, :self.n_act], dim=1))            # NNet.py:94
         v = torch.tanh(out[:, self.n_act])
         return pi, v

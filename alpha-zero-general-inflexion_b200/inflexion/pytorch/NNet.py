@@ -101,6 +101,16 @@ class NNetWrapper(NeuralNet):
             self._folded = FoldedInference(self.nnet, self.infer_dtype)
         return self._folded(planes)
 
+    def predict_head(self, planes: torch.Tensor, out: torch.Tensor):
+        """float32 [B,4,7,7] -> raw head output written into ``out`` (float16 [B,344]: 343 policy logits + the value
+        pre-activation).  For ``SelfPlayEngine(fused_head=True)``: the tree kernel applies softmax and tanh."""
+        if self._folded is None:
+            self.nnet.eval()
+            self._folded = FoldedInference(self.nnet, self.infer_dtype)
+        if self._folded.dtype != torch.float16:
+            raise ValueError("predict_head needs float16 inference (the kernel reads binary16 rows)")
+        return self._folded.head_into(planes, out)
+
     def weights_changed(self):
         self._folded = None
 

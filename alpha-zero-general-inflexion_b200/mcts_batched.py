@@ -31,7 +31,9 @@ def default_pool_size(num_sims: int) -> int:
 
 class BatchedMCTS:
     def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | None = None,
-                 max_depth: int = 32, backend: Backend | None = None):
+                 max_depth: int = 32, backend: Backend | None = None, fused_head: bool = False):
+        """fused_head: the net hands over its last GEMM output (float16 [G,344]: 343 policy logits + the value
+        pre-activation, buffer ``nn_head``) and the tree kernel applies softmax / tanh itself."""
         self.be = backend or default_backend()
         self.n_games, self.num_sims = int(n_games), int(num_sims)
         nodes = int(nodes_per_game or default_pool_size(num_sims))
@@ -41,7 +43,7 @@ class BatchedMCTS:
         # float32(cpuct): the reference multiplies a Python number into a float32 (NEP-50 weak scalar, MCTS.py:122)
         self.cfg = _capi.MctsConfig(n_games=self.n_games, nodes_per_game=nodes, hash_per_game=hash_slots,
                                     max_depth=max_depth, num_sims=self.num_sims, cpuct=float(np.float32(cpuct)),
-                                    seed=int(seed) & (2 ** 64 - 1), policy_is_logits=0, reserved=0)
+                                    seed=int(seed) & (2 ** 64 - 1), policy_is_logits=2 if fused_head else 0, reserved=0)
         dll = self.be.dll
         self.layout = _capi.MctsLayout()
         self.be.check(dll.ifx_mcts_get_layout(C.byref(self.cfg), C.byref(self.layout)))
@@ -59,6 +61,8 @@ class BatchedMCTS:
         self._nn_pi_rows = self.be.zeros((g, 352), torch.float32)    # rows padded to 352 floats: 16-byte aligned
         self.nn_pi = self._nn_pi_rows[:, :343]
         self.nn_v = self.be.zeros((g,), torch.float32)
+        self.fused_head = bool(fused_head)
+        self.nn_head = self.be.zeros((g, 344), torch.float16) if fused_head else None
         self.waves_run = 0
         self.evals_run = 0
 
@@ -93,20 +97,31 @@ class BatchedMCTS:
 
     # ---- search ---------------------------------------------------------------------------------
     def wave(self) -> None:
-        self.be.check(self.be.dll.ifx_mcts_wave(self._h, self.nn_pi.data_ptr(), self.nn_pi.stride(0),
-                                                self.nn_v.data_ptr(), self.nn_in.data_ptr(), self.be.stream()))
+        if self.fused_head:
+            self.be.check(self.be.dll.ifx_mcts_wave(self._h, self.nn_head.data_ptr(), self.nn_head.stride(0), None,
+                                                    self.nn_in.data_ptr(), self.be.stream()))
+        else:
+            self.be.check(self.be.dll.ifx_mcts_wave(self._h, self.nn_pi.data_ptr(), self.nn_pi.stride(0),
+                                                    self.nn_v.data_ptr(), self.nn_in.data_ptr(), self.be.stream()))
         self.waves_run += 1
 
-    def search(self, evaluate) -> None:
-        """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync."""
-        for _ in range(self.num_sims):
-            self.wave()
+    def feed(self, evaluate) -> None:
+        """One net evaluation of the pending leaves into the buffers the next wave reads."""
+        if self.fused_head:
+            evaluate(self.nn_in, self.nn_head)              # writes float16 [G,344] in place
+        else:
             pi, v = evaluate(self.nn_in)
             if pi is not self.nn_pi:
                 self.nn_pi.copy_(pi)
             if v is not self.nn_v:
                 self.nn_v.copy_(v.reshape(-1))
-            self.evals_run += 1
+        self.evals_run += 1
+
+    def search(self, evaluate) -> None:
+        """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync."""
+        for _ in range(self.num_sims):
+            self.wave()
+            self.feed(evaluate)
         self.wave()
 
     def search_adaptive(self, evaluate) -> None:
@@ -117,12 +132,7 @@ class BatchedMCTS:
             self.wave()
             if not bool(self.status()[:, 1].any()):
                 return
-            pi, v = evaluate(self.nn_in)
-            if pi is not self.nn_pi:
-                self.nn_pi.copy_(pi)
-            if v is not self.nn_v:
-                self.nn_v.copy_(v.reshape(-1))
-            self.evals_run += 1
+            self.feed(evaluate)
 
     def wave_timing(self, enable: bool) -> None:
         """Bracket every (un-captured) wave launch with CUDA events inside the library call (see ifx_mcts_wave_timing)."""
@@ -156,6 +166,11 @@ class BatchedMCTS:
         assert actions.dtype == torch.int32 and actions.shape == (self.n_games,)
         self.be.check(self.be.dll.ifx_mcts_advance(self._h, actions.data_ptr(), self.be.stream()))
         self._keep_a = actions
+
+    def restart_finished(self, tag_stride: int, count: torch.Tensor | None = None) -> None:
+        """New episode (start position, empty tree, RNG stream id + tag_stride) for every game that is over."""
+        self.be.check(self.be.dll.ifx_mcts_restart_finished(self._h, int(tag_stride), None if count is None else count.data_ptr(),
+                                                            self.be.stream()))
 
     def status(self) -> torch.Tensor:
         """int32 [G,8]: sims_done, pending, fault bits, move index, root outcome, live nodes, free nodes, path length."""

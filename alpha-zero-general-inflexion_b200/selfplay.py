@@ -25,17 +25,29 @@ from .state import STATE_DTYPE, pack_states
 class SelfPlayEngine:
     def __init__(self, n_games: int, num_sims: int, evaluate, cpuct=1.0, temp_threshold: int = 30, seed: int = 0,
                  max_turns: int = 343, game_id_base: int = 0, nodes_per_game: int | None = None,
-                 record: bool = True, use_graph: bool | None = None, backend: Backend | None = None):
-        """evaluate(nn_in f32 [G,4,7,7]) -> (pi f32 [G,343], v f32 [G]) on the device (e.g. nnet.predict_batch)."""
+                 record: bool = True, use_graph: bool | None = None, backend: Backend | None = None,
+                 fused_head: bool = False, auto_restart: bool = False, restart_stride: int | None = None,
+                 record_moves: int | None = None):
+        """evaluate(nn_in f32 [G,4,7,7]) -> (pi f32 [G,343], v f32 [G]) on the device (e.g. nnet.predict_batch); with
+        ``fused_head`` it is evaluate(nn_in, out f16 [G,344]) writing the raw head output (e.g. nnet.predict_head) and
+        the tree kernel does the softmax / tanh.  ``auto_restart``: a game that ends starts its next episode at once
+        (continuous self-play, Coach.py:108-112) with RNG stream id + ``restart_stride`` (default: n_games; pass the
+        global game count when several ranks play)."""
         self.be = backend or default_backend()
         self.G, self.num_sims, self.temp_threshold = int(n_games), int(num_sims), int(temp_threshold)
         self.max_turns, self.game_id_base = int(max_turns), int(game_id_base)
         self.evaluate = evaluate
-        self.mcts = BatchedMCTS(self.G, num_sims, cpuct, seed=seed, nodes_per_game=nodes_per_game, backend=self.be)
+        self.mcts = BatchedMCTS(self.G, num_sims, cpuct, seed=seed, nodes_per_game=nodes_per_game, backend=self.be,
+                                fused_head=fused_head)
         self.record = record
-        self.max_moves = self.max_turns + 1                      # a game lasts at most max_turns+1 moves
+        # a game lasts at most max_turns+1 moves; continuous play (auto_restart) records up to ``record_moves`` moves
+        self.max_moves = int(record_moves or self.max_turns + 1)
+        self.auto_restart = bool(auto_restart)
+        self.restart_stride = int(restart_stride or self.G)
+        self.restarts = self.be.zeros((1,), torch.int32)         # episodes finished and restarted so far
         if record:
             self.ex_states = self.be.empty((self.max_moves, self.G, 64), torch.uint8)
+            self.ex_after = self.be.empty((self.max_moves, self.G, 64), torch.uint8)   # root after the move (its outcome)
             self.ex_counts = self.be.empty((self.max_moves, self.G, 343), torch.int32)
             self.ex_actions = self.be.empty((self.max_moves, self.G), torch.int32)
         self.use_graph = self.be.is_cuda if use_graph is None else bool(use_graph)
@@ -55,24 +67,26 @@ class SelfPlayEngine:
 
     def _wave_and_net(self) -> None:
         self.mcts.wave()
-        pi, v = self.evaluate(self.mcts.nn_in)
-        if pi is not self.mcts.nn_pi:
-            self.mcts.nn_pi.copy_(pi)
-        if v is not self.mcts.nn_v:
-            self.mcts.nn_v.copy_(v.reshape(-1))
+        self.mcts.feed(self.evaluate)
 
     def _capture(self) -> None:
-        """One (tree wave, net forward) pair as a CUDA graph; replayed num_sims times per move."""
+        """The whole search of one move -- num_sims x (tree wave, net forward) + the closing wave -- as ONE CUDA
+        graph: a single launch per move, no host involvement and no inter-launch gaps inside it."""
         s = torch.cuda.Stream(device=self.be.device)
         s.wait_stream(torch.cuda.current_stream(self.be.device))
         with torch.cuda.stream(s):
-            for _ in range(2):                                   # warm the allocator / cuDNN heuristics on real data
-                pi, v = self.evaluate(self.mcts.nn_in)
+            for _ in range(2):                                   # warm the allocator / cuDNN heuristics (results unused)
+                if self.mcts.fused_head:
+                    self.evaluate(self.mcts.nn_in, torch.empty_like(self.mcts.nn_head))
+                else:
+                    self.evaluate(self.mcts.nn_in)
         torch.cuda.current_stream(self.be.device).wait_stream(s)
         torch.cuda.synchronize(self.be.device)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._wave_and_net()
+            for _ in range(self.num_sims):
+                self._wave_and_net()
+            self.mcts.wave()
 
     def search(self, wave_timer=None) -> None:
         """The numMCTSSims loop for all games.  ``wave_timer`` (optional): True launches every tree wave outside the
@@ -83,9 +97,7 @@ class SelfPlayEngine:
         if self.use_graph and wave_timer is None:
             if self._graph is None:
                 self._capture()
-            for _ in range(self.num_sims):
-                self._graph.replay()
-            self.mcts.wave()
+            self._graph.replay()
         elif wave_timer is None:
             for _ in range(self.num_sims):
                 self._wave_and_net()
@@ -98,25 +110,9 @@ class SelfPlayEngine:
         self.my_launches += self.num_sims + 1
 
     def _net_only(self) -> None:
-        if self.use_graph:
-            if getattr(self, "_net_graph", None) is None:
-                s = torch.cuda.Stream(device=self.be.device)
-                s.wait_stream(torch.cuda.current_stream(self.be.device))
-                with torch.cuda.stream(s):
-                    for _ in range(2):
-                        self.evaluate(self.mcts.nn_in)
-                torch.cuda.current_stream(self.be.device).wait_stream(s)
-                torch.cuda.synchronize(self.be.device)
-                self._net_graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._net_graph):
-                    pi, v = self.evaluate(self.mcts.nn_in)
-                    self.mcts.nn_pi.copy_(pi)
-                    self.mcts.nn_v.copy_(v.reshape(-1))
-            self._net_graph.replay()
-        else:
-            pi, v = self.evaluate(self.mcts.nn_in)
-            self.mcts.nn_pi.copy_(pi)
-            self.mcts.nn_v.copy_(v.reshape(-1))
+        """Net forward as plain stream launches (timed mode): the stream stays continuously fed, so the event pair
+        around the following tree wave brackets the kernel and not the turnaround after a graph launch."""
+        self.mcts.feed(self.evaluate)
 
     def finish_move(self) -> torch.Tensor:
         """Record the example of this move, choose the action, play it.  Returns the actions (int32 [G], -1 = over)."""
@@ -133,6 +129,12 @@ class SelfPlayEngine:
             self.my_launches += 1
         m.advance(acts)
         self.my_launches += 1
+        if self.record and self.move < self.max_moves:
+            self.be.check(self.be.dll.ifx_mcts_get_roots(m._h, self.ex_after[self.move].data_ptr(), self.be.stream()))
+            self.my_launches += 1
+        if self.auto_restart:
+            m.restart_finished(self.restart_stride, self.restarts)
+            self.my_launches += 1
         self.move += 1
         return acts
 
@@ -155,11 +157,16 @@ class SelfPlayEngine:
 
     # ---- host-buffer step (the end-to-end form measured by bench.py) ---------------------------------
     def step_host(self, roots_host: torch.Tensor, counts_host: torch.Tensor, actions_host: torch.Tensor,
-                  next_roots_host: torch.Tensor) -> None:
+                  next_roots_host: torch.Tensor, new_episode_host: torch.Tensor | None = None) -> None:
         """getActionProb + action choice + to_next_state for G games given as pinned HOST buffers: copies the root
-        states in, searches, copies visit counts, actions and next states out, and synchronises."""
+        states in, searches, copies visit counts, actions and next states out, and synchronises.
+        ``new_episode_host`` (int32 [G], optional) marks games whose root starts a new episode: their trees are
+        emptied first, as Coach.learn builds a fresh MCTS per episode (Coach.py:109-110)."""
         dev_roots = roots_host.to(self.be.device, non_blocking=True)
         self.mcts.set_roots(dev_roots)
+        if new_episode_host is not None:
+            self.mcts.reset(dev_roots, which=new_episode_host.to(self.be.device, non_blocking=True))
+            self.my_launches += 1
         self.search()
         stats = self.mcts.root_stats()
         acts = self.mcts.sample_actions(self.temp_threshold)
@@ -174,51 +181,59 @@ class SelfPlayEngine:
 
     # ---- training examples (Coach.py:74-90) ----------------------------------------------------------
     def examples(self, games=None, fix_alignment: bool = False, expand_symmetries: bool = True):
-        """-> (planes int64 [E,4,7,7], pi float64 [E,343], v float64 [E]) for the selected finished games, in the
-        reference's order: per game, per move, the 36 symmetric forms (Coach.py:77-78,89-90).
+        """-> (planes int64 [E,4,7,7], pi float64 [E,343], v float64 [E]) for every FINISHED episode of the selected
+        game slots, in the reference's order: per episode, per move, the 36 symmetric forms (Coach.py:77-78,89-90).
 
         Value targets follow Coach.py:89-90.  The reference extends ``players`` by the cumulative example count
         (Coach.py:79), so entry i of the zip pairs example i with players[i] where players = [P1]*36 + [P2]*72 +
         [P1]*108 + ...; that quirk is reproduced unless ``fix_alignment``."""
         assert self.record
-        n_moves = self.move
+        n_moves = min(self.move, self.max_moves)
         st_all = self.ex_states[:n_moves].cpu().numpy().view(STATE_DTYPE).reshape(n_moves, self.G)
-        final = self.mcts.roots().cpu().numpy().view(STATE_DTYPE).reshape(self.G)
+        after_all = self.ex_after[:n_moves].cpu().numpy().view(STATE_DTYPE).reshape(n_moves, self.G)
+        acts_all = self.ex_actions[:n_moves].cpu().numpy()
         games = range(self.G) if games is None else games
         out_planes, out_pi, out_v = [], [], []
         value_of = {0: 0.0, 1: 1e-4, 2: 1.0, 3: -1.0}
         for g in games:
-            played = int((self.ex_actions[:n_moves, g] >= 0).sum())
-            if played == 0:
-                continue
-            states = torch.from_numpy(np.ascontiguousarray(st_all[:played, g]).view(np.uint8).reshape(played, 64)).to(self.be.device)
-            planes = rules.planes(states, dtype=torch.int64, backend=self.be)
-            counts = self.ex_counts[:played, g].to(torch.float64)
-            moves = torch.arange(played, device=self.be.device)
-            temp1 = (moves + 1) < self.temp_threshold
-            pi = counts / counts.sum(dim=1, keepdim=True)
-            acts = self.ex_actions[:played, g].long()
-            onehot = torch.zeros_like(pi)
-            onehot[moves, acts] = 1.0
-            pi = torch.where(temp1[:, None], pi, onehot)
-            if expand_symmetries:
-                planes = rules.symmetries(planes.contiguous(), backend=self.be).reshape(-1, 4, 7, 7)
-                pi = rules.symmetries(pi.reshape(played, 7, 7, 7).contiguous(), backend=self.be).reshape(-1, 343)
-                per = 36
-            else:
+            start = 0
+            for mv in range(n_moves):
+                if acts_all[mv, g] < 0:                       # slot idle (game over, no restart)
+                    start = mv + 1
+                    continue
+                if after_all[mv, g]["outcome"] == 0:
+                    continue
+                rows = np.arange(start, mv + 1)               # one finished episode: moves start..mv of slot g
+                start = mv + 1
+                played = len(rows)
+                states = torch.from_numpy(np.ascontiguousarray(st_all[rows, g]).view(np.uint8).reshape(played, 64)).to(self.be.device)
+                planes = rules.planes(states, dtype=torch.int64, backend=self.be)
+                counts = self.ex_counts[rows[0]:rows[-1] + 1, g].to(torch.float64)
+                moves = torch.arange(played, device=self.be.device)
+                temp1 = (moves + 1) < self.temp_threshold
+                pi = counts / counts.sum(dim=1, keepdim=True)
+                acts = self.ex_actions[rows[0]:rows[-1] + 1, g].long()
+                onehot = torch.zeros_like(pi)
+                onehot[moves, acts] = 1.0
+                pi = torch.where(temp1[:, None], pi, onehot)
                 per = 1
-            # side to move of each recorded state vs the side to move at the end
-            movers = np.where(st_all[:played, g]["player"] == 0, 1, -1)
-            end_player = 1 if final[g]["player"] == 0 else -1
-            result = value_of[int(final[g]["outcome"])]
-            if fix_alignment or per == 1:
-                players = np.repeat(movers, per)
-            else:
-                players = np.concatenate([np.full(per * (i + 1), movers[i]) for i in range(played)])[: per * played]
-            v = np.where(players == end_player, result, -result)
-            out_planes.append(planes.cpu().numpy())
-            out_pi.append(pi.cpu().numpy())
-            out_v.append(v.astype(np.float64))
+                if expand_symmetries:
+                    planes = rules.symmetries(planes.contiguous(), backend=self.be).reshape(-1, 4, 7, 7)
+                    pi = rules.symmetries(pi.reshape(played, 7, 7, 7).contiguous(), backend=self.be).reshape(-1, 343)
+                    per = 36
+                # side to move of each recorded state vs the side to move at the end
+                movers = np.where(st_all[rows, g]["player"] == 0, 1, -1)
+                final = after_all[mv, g]
+                end_player = 1 if final["player"] == 0 else -1
+                result = value_of[int(final["outcome"])]
+                if fix_alignment or per == 1:
+                    players = np.repeat(movers, per)
+                else:
+                    players = np.concatenate([np.full(per * (i + 1), movers[i]) for i in range(played)])[: per * played]
+                v = np.where(players == end_player, result, -result)
+                out_planes.append(planes.cpu().numpy())
+                out_pi.append(pi.cpu().numpy())
+                out_v.append(v.astype(np.float64))
         if not out_planes:
             return np.zeros((0, 4, 7, 7), np.int64), np.zeros((0, 343)), np.zeros(0)
         return np.concatenate(out_planes), np.concatenate(out_pi), np.concatenate(out_v)

@@ -174,7 +174,8 @@ def run_reference(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "games_per_s": value / (a.sims * MOVES_PER_GAME),
-        "config": workload_config(a, per_gpu_games=procs, note="CPU arm: one game per host core"),
+        "config": workload_config(a, a.games, note=f"CPU arm: bounded sample of this workload, {procs} games (one per host core) "
+                                                    f"x {a.sims} sims per step"),
         "cpu_baseline": {"value": value, "unit": "sims/s", "cores": procs, "kind": "port",
                          "sample": f"{procs} processes x {len(timed)} moves x {a.sims} sims (oracle port of the reference "
                                    f"MCTS+rules, {a.net} net on CPU, 1 torch thread per process)"},
@@ -229,12 +230,13 @@ def run_ours(a):
         torch.manual_seed(0)
         torch.backends.cudnn.benchmark = True
         nnet = NNetWrapper(InflexionGame(7, max_turns=343, max_power=6), device=be.device)
-        evaluate = nnet.predict_batch
+        evaluate, fused = nnet.predict_head, True          # last GEMM -> tree kernel (softmax/tanh fused there)
     else:
-        evaluate = lambda x: stub_policy_value(x)  # noqa: E731
+        evaluate, fused = (lambda x: stub_policy_value(x)), False  # noqa: E731
 
     eng = SelfPlayEngine(a.games, a.sims, evaluate, cpuct=1.0, temp_threshold=30, seed=2023, max_turns=343,
-                         game_id_base=rank * a.games, record=True, backend=be)
+                         game_id_base=rank * a.games, record=True, backend=be, fused_head=fused,
+                         auto_restart=True, restart_stride=world * a.games)
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,47 +248,59 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         eng.play_move()
     eng.mcts.raise_on_faults()
-    # per-wave event timing path (wave launched outside the graph, bracketed by events inside the library call)
-    eng.mcts.wave_timing(True)
-    eng.play_move(True)
-    eng.mcts.wave_time()
-    # ---- timed region: K steps, device-resident ---------------------------------------------------------
-    c0 = eng.mcts.counters()
+    # ---- timed region: EXACTLY K steps, device-resident, one CUDA-graph launch per move -------------------------
     l0 = eng.my_launches
+    c0 = eng.mcts.counters()
     barrier()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         t_start.record()
-        tree_ms, n_tree = 0.0, 0
-        for k in range(a.steps):
-            eng.play_move(True)
-            if (k + 1) % 30 == 0:                          # drain the library's event ring (4096 pairs) before it fills
-                ms, n = eng.mcts.wave_time()
-                tree_ms, n_tree = tree_ms + ms, n_tree + n
+        for _ in range(a.steps):
+            eng.play_move()
         t_end.record()
         barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
     c1 = eng.mcts.counters()
     eng.mcts.raise_on_faults()
     launches = eng.my_launches - l0
-    ms, n = eng.mcts.wave_time()                           # CUDA events recorded around every wave launch
-    tree_ms, n_tree = tree_ms + ms, n_tree + n
-    eng.mcts.wave_timing(False)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=be.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t[0])
     sims_rank = c1["sims"] - c0["sims"]
-    visits, expansions = c1["node_visits"] - c0["node_visits"], c1["expansions"] - c0["expansions"]
     sims_total = sims_rank * world                     # every rank runs the same amount of work (weak scaling)
     value = sims_total / (elapsed_ms * 1e-3)
 
-    # roofline of OUR dominant kernel (tree wave): algorithmic bytes / measured kernel time
+    # ---- instrumented pass: the same K steps again with every tree wave launched outside the graph and bracketed by
+    # CUDA events recorded inside the library call on the launching stream (roofline of OUR dominant kernel) -------
+    eng.mcts.wave_timing(True)
+    eng.play_move(True)                                    # warm the un-captured path
+    eng.mcts.wave_time()
+    c2 = eng.mcts.counters()
+    torch.cuda.synchronize()
+    i_start, i_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i_start.record()
+    tree_ms, n_tree = 0.0, 0
+    for k in range(a.steps):
+        eng.play_move(True)
+        if (k + 1) % 30 == 0:                              # drain the library's event ring (4096 pairs) before it fills
+            ms, n = eng.mcts.wave_time()
+            tree_ms, n_tree = tree_ms + ms, n_tree + n
+    i_end.record()
+    torch.cuda.synchronize()
+    ms, n = eng.mcts.wave_time()
+    tree_ms, n_tree = tree_ms + ms, n_tree + n
+    eng.mcts.wave_timing(False)
+    instr_ms = i_start.elapsed_time(i_end)
+    c3 = eng.mcts.counters()
+    visits, expansions = c3["node_visits"] - c2["node_visits"], c3["expansions"] - c2["expansions"]
+    sims_instr = c3["sims"] - c2["sims"]
     tree_bytes = TREE_BYTES_PER_VISIT * visits + TREE_BYTES_PER_EXPANSION * expansions
     tree_gbs = tree_bytes / (tree_ms * 1e-3) / 1e9 if tree_ms > 0 else 0.0
-    net_ms = elapsed_ms - tree_ms
+    net_ms = instr_ms - tree_ms
     net_evals = a.games * a.sims * a.steps
     net_tflops = net_evals * NET_FLOP_PER_EVAL / (net_ms * 1e-3) / 1e12 if a.net == "default" and net_ms > 0 else None
+    sims_rank = max(sims_instr, 1)
 
     # ---- end to end through the public host-buffer API ----------------------------------------------------
     e2e = None
@@ -297,21 +311,38 @@ def run_ours(a):
         acts_h = torch.empty((a.games,), dtype=torch.int32).pin_memory()
         roots_h.copy_(eng.mcts.roots())
         torch.cuda.synchronize()
-        eng.step_host(roots_h, counts_h, acts_h, next_h)          # warm
-        roots_h.copy_(next_h)
+        restart_h = torch.zeros((a.games,), dtype=torch.int32).pin_memory()
+        start_state = torch.from_numpy(np.ascontiguousarray(
+            __import__("inflexion_b200").state.pack_states(np.zeros((1, 49), dtype=np.int64), 1, 0, 0, 343)).view(np.uint8).reshape(64))
+        next_id = [(world + rank) * a.games * 1000]
+
+        def hand_over():
+            """host side of the loop: next positions become the roots; finished games start a new episode"""
+            roots_h.copy_(next_h)
+            restart_h.copy_(roots_h[:, 45] != 0)
+            over = torch.nonzero(restart_h).flatten()
+            for g in over.tolist():
+                roots_h[g] = start_state
+                roots_h[g, 48:52] = torch.from_numpy(np.array([next_id[0]], dtype=np.uint32).view(np.uint8))
+                next_id[0] += 1
+        eng.step_host(roots_h, counts_h, acts_h, next_h, restart_h)   # warm
+        hand_over()
         barrier()
         k2 = max(2, min(a.steps, 4))
+        ce0 = eng.mcts.counters()
         t0 = time.perf_counter()
         for _ in range(k2):
-            eng.step_host(roots_h, counts_h, acts_h, next_h)
-            roots_h.copy_(next_h)                                 # host-side hand-over of the next positions
+            eng.step_host(roots_h, counts_h, acts_h, next_h, restart_h)
+            hand_over()
         barrier()
         dt = time.perf_counter() - t0
+        ce1 = eng.mcts.counters()
         if world > 1:
             t = torch.tensor([dt], device=be.device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
-        e2e = {"value": a.games * a.sims * k2 * world / dt, "unit": "sims/s", "h2d_bytes_per_step": a.games * 64,
+        e2e_sims = (ce1["sims"] - ce0["sims"]) * world
+        e2e = {"value": e2e_sims / dt, "unit": "sims/s", "h2d_bytes_per_step": a.games * (64 + 4),
                "d2h_bytes_per_step": a.games * (343 * 4 + 4 + 64), "steps": k2,
                "api": "SelfPlayEngine.step_host(pinned host roots) -> host visit counts, actions, next roots"}
 
@@ -325,11 +356,14 @@ def run_ours(a):
             "roofline": {"kernel": "tree_wave_kernel", "bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": tree_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": tree_bytes / max(n_tree, 1), "avg_launch_us": 1e3 * tree_ms / max(n_tree, 1),
-                         "launches": n_tree, "share_of_step": tree_ms / elapsed_ms,
+                         "launches": n_tree, "share_of_step": tree_ms / instr_ms,
+                         "measured_in": "instrumented pass of the same K steps (waves outside the CUDA graph, event pairs recorded "
+                                        "inside ifx_mcts_wave)",
                          "visits_per_sim": visits / max(sims_rank, 1), "expansions_per_sim": expansions / max(sims_rank, 1)},
             "roofline_net": None if net_tflops is None else {
                 "kernel": "policy-value net forward (cuDNN/cuBLAS fp16, library)", "bound": "tensor", "achieved": net_tflops,
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": net_tflops / tensor_peak, "share_of_step": net_ms / elapsed_ms},
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": net_tflops / tensor_peak, "share_of_step": net_ms / instr_ms,
+                "note": "everything in the instrumented pass that is not the tree wave; peak = measured sustained bf16 GEMM rate (fp16 has the same nominal rate)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         if world == 1 and not a.no_cpu_baseline:

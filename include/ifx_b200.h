@@ -124,8 +124,10 @@ typedef struct ifx_mcts_config {
   int32_t num_sims;         /* args.numMCTSSims (MCTS.py:45)                                      */
   float cpuct;              /* float32(args.cpuct) (MCTS.py:122; NEP-50 weak scalar)              */
   uint64_t seed;            /* Philox key for every random draw on the path    */
-  int32_t policy_is_logits; /* 0: nn_pi holds probabilities (NNet.py:94 exp(log_softmax));
-                               1: nn_pi holds raw logits, softmax fused into the expansion        */
+  int32_t policy_is_logits; /* 0: nn_pi holds float32 probabilities (NNet.py:94 exp(log_softmax)), nn_v values;
+                               2: nn_pi points at the net's last GEMM output, binary16 rows of pi_stride
+                                  (>= 344, multiple of 4) halfs = 343 policy logits + the value pre-activation;
+                                  softmax and tanh are fused into the expansion, nn_v is ignored           */
   int32_t reserved;
 } ifx_mcts_config;
 
@@ -198,6 +200,11 @@ IFX_API int ifx_mcts_sample_actions(ifx_mcts* m, int32_t temp_threshold, int32_t
 
 /* game = game.to_next_state(action) for every game (Coach.py:82) and start the next move. */
 IFX_API int ifx_mcts_advance(ifx_mcts* m, const int32_t* actions, void* stream);
+
+/* Continuous self-play (Coach.learn starts the next episode when one ends, Coach.py:108-112): every game whose
+ * root is terminal gets the start position, an empty tree and the RNG stream tag + tag_stride; *count (nullable,
+ * device int32) is incremented once per restarted game. */
+IFX_API int ifx_mcts_restart_finished(ifx_mcts* m, uint32_t tag_stride, int32_t* count, void* stream);
 
 /* status int32 [G][8]: sims_done, pending, fault bits, move index, root outcome, live nodes, free nodes, 0. */
 IFX_API int ifx_mcts_status(ifx_mcts* m, int32_t* status, void* stream);

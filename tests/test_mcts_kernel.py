@@ -163,3 +163,31 @@ def test_pool_exhaustion_is_reported(backend):
     m.search(stub_eval("float"))
     with pytest.raises(Exception, match="pool"):
         m.raise_on_faults()
+
+
+def test_fused_head_softmax_matches_torch(backend):
+    """fused-head mode: the kernel's softmax / tanh of the net's binary16 head output against torch's
+    exp(log_softmax) / tanh (NNet.py:94, InflexionNNet.py:54), then masked renormalisation -- float32 tolerance."""
+    G = 5
+    m = BatchedMCTS(G, 3, 1.0, seed=3, backend=backend, fused_head=True)
+    m.reset(start_states(G, 343))
+    gen = torch.Generator().manual_seed(0)
+    head = (torch.randn(G, 344, generator=gen) * 3).to(torch.float16)
+
+    def evaluate(nn_in, out):
+        out.copy_(head.to(out.device))
+    m.search(evaluate)
+    m.raise_on_faults()
+    tv = m.table_views()
+    x = head.float()
+    probs = torch.exp(torch.log_softmax(x[:, :343], dim=1))
+    valid = torch.zeros(343); valid[294:] = 1                      # empty board: the 49 spawn actions
+    want = (probs * valid) / (probs * valid).sum(dim=1, keepdim=True)
+    for g in range(G):
+        keys = tv["key"][g]
+        root = [s for s in np.nonzero(keys[:, 0] != np.uint64(2 ** 64 - 1))[0] if (int(keys[s, 0]) >> 49) == 0][0]
+        got = torch.from_numpy(tv["P"][g, root].copy())
+        assert torch.allclose(got, want[g], rtol=2e-5, atol=1e-8)
+    # the root was expanded with v = tanh(head[:, 343]); its children were then visited twice
+    counts = m.root_stats()["counts"].cpu().numpy()
+    assert counts.sum(axis=1).tolist() == [2] * G

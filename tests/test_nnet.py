@@ -136,3 +136,20 @@ def test_16bit_folded_inference_within_tolerance_on_gpu():
         lp, v = net(x)
     pi, vv = FoldedInference(net)(x)
     assert float((pi - torch.exp(lp)).abs().max()) < tol and float((vv - v.reshape(-1)).abs().max()) < 5e-3
+
+
+@pytest.mark.gpu
+def test_head_into_equals_call_on_gpu():
+    """predict_head hands the raw binary16 head output to the tree kernel; with softmax/tanh applied it must equal
+    the ordinary predict_batch output."""
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    net = InflexionNNet(Shape(), dotdict({"num_channels": 512, "dropout": 0.3})).to(dev).eval()
+    f = FoldedInference(net)
+    x = torch.from_numpy(random_planes(512, seed=5)).to(dev)
+    pi, v = f(x)
+    out = torch.empty(512, 344, dtype=torch.float16, device=dev)
+    f.head_into(x, out)
+    pi2 = torch.exp(torch.log_softmax(out[:, :343].float(), dim=1))
+    v2 = torch.tanh(out[:, 343].float())
+    assert torch.allclose(pi, pi2, atol=1e-6) and torch.allclose(v, v2, atol=1e-6)

@@ -39,3 +39,26 @@ def test_many_games_lockstep_and_restart(backend):
     eng.restart()
     assert eng.play_episode() == moves
     assert np.array_equal(eng.ex_actions[:moves].cpu().numpy(), first)        # same seed, same game ids -> same games
+
+
+def test_continuous_selfplay_restarts_finished_games(backend):
+    """auto_restart: a finished game starts its next episode at once on a fresh RNG stream; every finished episode
+    yields its examples, and the first episode of each slot is the same game a run without restarts plays."""
+    kw = dict(cpuct=1.0, temp_threshold=3, seed=4, max_turns=4, game_id_base=40, backend=backend)
+    base = SelfPlayEngine(4, 10, lambda x: stub_policy_value(x), **kw)
+    n0 = base.play_episode()
+    eng = SelfPlayEngine(4, 10, lambda x: stub_policy_value(x), auto_restart=True, restart_stride=1000, record_moves=16, **kw)
+    for _ in range(12):
+        eng.play_move()
+    eng.mcts.raise_on_faults()
+    assert np.array_equal(eng.ex_actions[:n0].cpu().numpy()[base.ex_actions[:n0].cpu().numpy() >= 0],
+                          base.ex_actions[:n0].cpu().numpy()[base.ex_actions[:n0].cpu().numpy() >= 0])
+    done = int(eng.restarts[0])
+    assert done >= 8                                            # games last at most 5 moves here
+    tags = eng.mcts.roots().cpu().numpy().view(np.uint32).reshape(4, 16)[:, 12]
+    assert all(int(t) >= 40 + 2000 for t in tags)               # every slot is on its third stream or later
+    planes, pi, v = eng.examples(expand_symmetries=False)
+    ep_first = (planes[:, 2, 0, 0] == 0).sum()                  # one turn-0 example per finished episode
+    assert ep_first == done and len(planes) >= done * 2 and np.allclose(pi.sum(axis=1), 1.0)
+    p0, pi0, v0 = base.examples(expand_symmetries=False)
+    assert len(p0) > 0
