@@ -92,6 +92,15 @@ class Coach:
             if i % pit_interval != 0:
                 continue
             log.info("PITTING AGAINST BASELINES")
+            if hasattr(self.nnet, "predict_batch"):
+                # all arenaCompare games of a pairing at once on the device (same players, same colour split)
+                from .arena_batched import BatchedArena
+                for name in ("random", "greedy"):
+                    arena = BatchedArena(self.nnet.predict_batch, int(self.args.numMCTSSims), self.args.cpuct, opponent=name,
+                                         seed=int(np.random.randint(0, 2 ** 31 - 1)), max_turns=self.game._max_turns)
+                    p1wins, p2wins, draws = arena.playGames(int(self.args.arenaCompare))
+                    log.info(f"NEW/{name.capitalize()}Player WINS : {p1wins} / {p2wins} ; DRAWS : {draws}")
+                continue
             player1 = MCTSPlayer(MCTS(self.nnet, self.args))
             for player2 in (RandomPlayer(), GreedyPlayer()):
                 arena = Arena(player1, player2, self.game.restarted())

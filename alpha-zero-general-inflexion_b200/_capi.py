@@ -38,6 +38,7 @@ PROTOTYPES = {
     "ifx_rules_symmetries": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "ifx_rules_transform": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "ifx_rules_random_actions": (c_int, [c_void_p, c_int64, c_uint64, C.c_uint32, c_void_p, c_void_p]),
+    "ifx_rules_greedy_actions": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ifx_rules_info": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ifx_rules_mask_step_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "ifx_rules_planes_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),

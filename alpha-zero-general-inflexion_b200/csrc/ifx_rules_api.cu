@@ -52,6 +52,24 @@ IFX_HD int rules_random_action_of(const ifx_state& s, uint64_t seed, uint32_t st
   return IFX_SPAWN * IFX_CELLS + rules_nth_bit(spawn, k - 6 * n_own);
 }
 
+// GreedyPlayer.play (InflexionPlayers.py:61-77): one-ply look-ahead on score() = #own - #opponent stacks from the
+// mover's side; candidates are sorted (score, action) descending, so ties go to the HIGHEST action index.
+IFX_HD int rules_greedy_action_of(const ifx_state& s) {
+  if (s.outcome != IFX_ONGOING) return -1;
+  const uint64_t own = ifx_own(s), spawn = ifx_spawn_mask(s);
+  int best = -1, best_score = -1000;
+  for (int a = 0; a < IFX_ACTIONS; ++a) {
+    const int m = a / IFX_CELLS, cell = a - m * IFX_CELLS;
+    if (!(((m == IFX_SPAWN ? spawn : own) >> cell) & 1ull)) continue;
+    ifx_state t = s;
+    ifx_apply(t, a);
+    // after the move the side to move is the opponent: mover's score = #opp(t) - #own(t)
+    const int score = ifx_popc64(ifx_opp(t)) - ifx_popc64(ifx_own(t));
+    if (score >= best_score) { best_score = score; best = a; }
+  }
+  return best;
+}
+
 // value of plane c at (symmetry-mapped) cell, as float
 IFX_HD int rules_plane_value(const ifx_state& s, int c, int src_cell) {
   switch (c) {
@@ -167,6 +185,16 @@ __global__ void rules_random_actions_kernel(const ifx_state* __restrict__ states
 #pragma unroll
   for (int c = 0; c < 4; ++c) a.q[c] = __ldg(p + c);
   actions[i] = rules_random_action_of(a.s, seed, a.s.tag, step);
+}
+
+__global__ void rules_greedy_actions_kernel(const ifx_state* __restrict__ states, int64_t n, int32_t* __restrict__ actions) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  union { ifx_state s; uint4 q[4]; } a;
+  const uint4* p = reinterpret_cast<const uint4*>(states + i);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) a.q[c] = __ldg(p + c);
+  actions[i] = rules_greedy_action_of(a.s);
 }
 
 __global__ void rules_info_kernel(const ifx_state* __restrict__ states, int64_t n, int32_t* __restrict__ info) {
@@ -289,6 +317,18 @@ int ifx_rules_random_actions(const ifx_state* states, int64_t n, uint64_t seed, 
   return IFX_OK;
 #else
   rules_random_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(states, n, seed, step, actions);
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_rules_greedy_actions(const ifx_state* states, int64_t n, int32_t* actions, void* stream) {
+  if (n < 0 || (n > 0 && (!states || !actions))) return IFX_E_ARG;
+  if (n == 0) return IFX_OK;
+#ifdef IFX_HOSTSIM
+  for (int64_t i = 0; i < n; ++i) actions[i] = rules_greedy_action_of(states[i]);
+  return IFX_OK;
+#else
+  rules_greedy_actions_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(states, n, actions);
   return ifx_after_launch();
 #endif
 }

@@ -75,6 +75,14 @@ def random_actions(states: torch.Tensor, seed: int, step: int, backend: Backend 
     return out
 
 
+def greedy_actions(states: torch.Tensor, backend: Backend | None = None) -> torch.Tensor:
+    """GreedyPlayer for every state: best one-ply score(), ties to the highest action -> int32 [S], -1 = game over."""
+    be = backend or default_backend()
+    out = be.empty((states.shape[0],), torch.int32)
+    be.check(be.dll.ifx_rules_greedy_actions(_ptr(states), states.shape[0], _ptr(out), be.stream()))
+    return out
+
+
 def info(states: torch.Tensor, backend: Backend | None = None) -> torch.Tensor:
     """-> int32 [S,4]: score, power_diff (side to move), total_power, number of valid actions."""
     be = backend or default_backend()

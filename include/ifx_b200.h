@@ -104,6 +104,10 @@ IFX_API int ifx_rules_info(const ifx_state* states, int64_t n, int32_t* info /* 
 IFX_API int ifx_rules_random_actions(const ifx_state* states, int64_t n, uint64_t seed, uint32_t step,
                                      int32_t* actions, void* stream);
 
+/* GreedyPlayer.play for every state (InflexionPlayers.py:61-77): best one-ply score(), ties to the highest
+ * action index; -1 for finished games. */
+IFX_API int ifx_rules_greedy_actions(const ifx_state* states, int64_t n, int32_t* actions, void* stream);
+
 /* Host-buffer forms of the above (plain host pointers; copies in, launches, copies out, synchronises).
  * These are what the object-per-game drop-in API (InflexionGame.to_next_state etc.) calls. */
 IFX_API int ifx_rules_mask_step_host(const ifx_state* states_in, const int32_t* actions, int64_t n,

@@ -92,3 +92,26 @@ def test_example_file_format_roundtrip(tmp_path):
     c2 = Coach(game, StubNet(), args)
     c2.loadTrainExamples()
     assert c2.skipFirstSelfPlay and len(c2.trainExamplesHistory[0]) == len(ex)
+
+
+def test_greedy_kernel_equals_greedy_player(backend):
+    from inflexion_b200 import rules
+    from inflexion_b200.state import pack_states
+    from oracle import inflexion_rules as R
+    b, p, t, _ = R.random_reachable_states(60, seed=8)
+    st = pack_states(b, p, t)
+    got = rules.greedy_actions(backend.states_tensor(st), backend=backend).cpu().numpy()
+    for i in range(60):
+        g = InflexionGame(7, curr_player=PlayerColour.RED if p[i] > 0 else PlayerColour.BLUE,
+                          board=b[i].astype(int).reshape(7, 7), curr_turn=int(t[i]), max_turns=343)
+        assert got[i] == GreedyPlayer().play(g)
+
+
+def test_batched_arena(backend):
+    from inflexion_b200.arena_batched import BatchedArena
+    ev = lambda x: stub_policy_value(x)  # noqa: E731
+    for opp in ("random", "greedy"):
+        arena = BatchedArena(ev, num_sims=6, opponent=opp, seed=3, max_turns=10, backend=backend)
+        one, two, dr = arena.playGames(7)
+        assert one + two + dr == 7
+        assert (one, two, dr) == BatchedArena(ev, num_sims=6, opponent=opp, seed=3, max_turns=10, backend=backend).playGames(7)
