@@ -457,6 +457,7 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   // speculative: they are only used when a leaf is pending, which is the common case)
   IfxGame G = P.games[g];
   const ifx_state leaf = P.leaves[g];
+  const ifx_state root = P.roots[g];                         // does not change within a wave
   float leaf_v;
   PolicyRegs pol;
   if (P.logits == 2) {                                      // binary16 head output: softmax + tanh fused here
@@ -483,10 +484,13 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
     if (P.debug) dbg_t3 = ifx_now_ns();
   }
   while (!G.faults && G.sims_done < P.num_sims) {
-    ifx_state st = P.roots[g];
+    ifx_state st = root;
     int depth = 0;
     int slot = G.root_slot;                                 // -1: the root is not expanded yet
     bool verified = slot >= 0;                              // the cached root slot needs no key check
+    RowRegs rows;
+    bool inflight = slot >= 0;
+    if (inflight) tree_rows_load(P, g, slot, rows);         // root rows: issued before anything else of this simulation
     for (;;) {
       if (st.outcome != IFX_ONGOING) {                      // MCTS.py:85-87: terminal, value is a Python number
         tree_backup_apply(P, g, depth, path, -ifx_outcome_value(st.outcome), false, -1);
@@ -494,14 +498,10 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
         break;
       }
       const uint64_t k0 = ifx_key0(st), k1 = ifx_key1(st);
-      RowRegs rows;
       int miss_pos = -1;
-      if (slot >= 0) {
-        // speculative: rows, header and key of the hinted slot in ONE round trip; the key decides whether the
-        // hint was right (the reference looks nodes up by planes, not by edge: SURVEY.md H1)
-        tree_rows_load(P, g, slot, rows);
-        if (!verified && !(rows.key.k0 == k0 && rows.key.k1 == k1)) slot = -1;
-      }
+      // the rows, header and key of the hinted slot were requested one step ago, in ONE round trip; the key decides
+      // whether the hint was right (the reference looks nodes up by planes, not by edge: SURVEY.md H1)
+      if (inflight && !verified && !(rows.key.k0 == k0 && rows.key.k1 == k1)) slot = -1;
       if (slot < 0) {
         slot = tree_hash_find(P, g, k0, k1, &miss_pos);
         dbg_probes += 1;
@@ -528,10 +528,13 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
       depth += 1;
       if (P.debug && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
       dbg_depth = depth > dbg_depth ? depth : dbg_depth;
-      ifx_apply(st, a);                                     // MCTS.py:132
+      // request the hinted child's rows BEFORE stepping the board: the loads fly while the rules run
       const uint32_t hint = (raw >> IFX_N_HINT_SHIFT) & IFX_N_HINT_NONE;
       slot = (hint != IFX_N_HINT_NONE && (int)hint < P.C) ? (int)hint : -1;
       verified = false;
+      inflight = slot >= 0;
+      if (inflight) tree_rows_load(P, g, slot, rows);
+      ifx_apply(st, a);                                     // MCTS.py:132
     }
     if (G.pending) break;
   }

@@ -116,10 +116,14 @@ IFX_D void body_status(const TreeParams& P, int g, int32_t* status) {
 }
 
 #ifndef IFX_HOSTSIM
-#define TREE_WARPS 4
+// One warp per CTA: a game's slot is handed to the next game the moment its simulation ends (with four warps per
+// CTA the three siblings of a deep game idle until it finishes).  20 resident CTAs per SM = 86 registers, no spills.
+#ifndef TREE_WARPS
+#define TREE_WARPS 1
+#endif
 #define TREE_BLOCK (TREE_WARPS * 32)
 #ifndef IFX_WAVE_MIN_BLOCKS
-#define IFX_WAVE_MIN_BLOCKS 5      // resident CTAs per SM the wave kernel is compiled for (register cap 65536/(128*n))
+#define IFX_WAVE_MIN_BLOCKS 20     // resident CTAs per SM the wave kernel is compiled for (register cap 65536/(32*n))
 #endif
 
 __global__ void __launch_bounds__(TREE_BLOCK, IFX_WAVE_MIN_BLOCKS)

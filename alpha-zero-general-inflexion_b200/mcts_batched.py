@@ -31,7 +31,8 @@ def default_pool_size(num_sims: int) -> int:
 
 class BatchedMCTS:
     def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | None = None,
-                 max_depth: int = 32, backend: Backend | None = None, fused_head: bool = False):
+                 max_depth: int = 32, backend: Backend | None = None, fused_head: bool = False,
+                 pad_policy_rows: bool = True):
         """fused_head: the net hands over its last GEMM output (float16 [G,344]: 343 policy logits + the value
         pre-activation, buffer ``nn_head``) and the tree kernel applies softmax / tanh itself."""
         self.be = backend or default_backend()
@@ -58,8 +59,11 @@ class BatchedMCTS:
         g = self.n_games
         # net I/O buffers (persistent so the wave + net step can be captured in a CUDA graph)
         self.nn_in = self.be.zeros((g, 4, 7, 7), torch.float32)
-        self._nn_pi_rows = self.be.zeros((g, 352), torch.float32)    # rows padded to 352 floats: 16-byte aligned
-        self.nn_pi = self._nn_pi_rows[:, :343]
+        if pad_policy_rows:
+            self._nn_pi_rows = self.be.zeros((g, 352), torch.float32)    # rows padded to 352 floats: 16-byte aligned
+            self.nn_pi = self._nn_pi_rows[:, :343]
+        else:                                                        # dense [G,343] rows (the kernel's scalar-load path)
+            self.nn_pi = self.be.zeros((g, 343), torch.float32)
         self.nn_v = self.be.zeros((g,), torch.float32)
         self.fused_head = bool(fused_head)
         self.nn_head = self.be.zeros((g, 344), torch.float16) if fused_head else None

@@ -191,3 +191,17 @@ def test_fused_head_softmax_matches_torch(backend):
     # the root was expanded with v = tanh(head[:, 343]); its children were then visited twice
     counts = m.root_stats()["counts"].cpu().numpy()
     assert counts.sum(axis=1).tolist() == [2] * G
+
+
+def test_dense_policy_rows_give_the_same_search(backend):
+    """nn_pi with a row stride of 343 floats (unaligned rows, scalar loads) == padded rows (128-bit loads)."""
+    out = []
+    for pad in (True, False):
+        m = BatchedMCTS(3, 15, 1.0, seed=8, backend=backend, pad_policy_rows=pad)
+        m.reset(start_states(3, 343))
+        m.search(stub_eval("float"))
+        m.raise_on_faults()
+        out.append(m.root_stats(want_q=True))
+    assert m.nn_pi.stride(0) == 343
+    for k in ("counts", "q32", "ns"):
+        assert torch.equal(out[0][k].cpu(), out[1][k].cpu())
