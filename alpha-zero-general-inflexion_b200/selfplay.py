@@ -189,12 +189,15 @@ class SelfPlayEngine:
         [P1]*108 + ...; that quirk is reproduced unless ``fix_alignment``."""
         assert self.record
         n_moves = min(self.move, self.max_moves)
+        dev = self.be.device
         st_all = self.ex_states[:n_moves].cpu().numpy().view(STATE_DTYPE).reshape(n_moves, self.G)
         after_all = self.ex_after[:n_moves].cpu().numpy().view(STATE_DTYPE).reshape(n_moves, self.G)
         acts_all = self.ex_actions[:n_moves].cpu().numpy()
-        games = range(self.G) if games is None else games
-        out_planes, out_pi, out_v = [], [], []
+        games = list(range(self.G) if games is None else games)
+        per = 36 if expand_symmetries else 1
         value_of = {0: 0.0, 1: 1e-4, 2: 1.0, 3: -1.0}
+        # 1. finished episodes: (slot, first move, last move); value targets per example (host, tiny)
+        sel_mv, sel_g, values = [], [], []
         for g in games:
             start = 0
             for mv in range(n_moves):
@@ -206,23 +209,7 @@ class SelfPlayEngine:
                 rows = np.arange(start, mv + 1)               # one finished episode: moves start..mv of slot g
                 start = mv + 1
                 played = len(rows)
-                states = torch.from_numpy(np.ascontiguousarray(st_all[rows, g]).view(np.uint8).reshape(played, 64)).to(self.be.device)
-                planes = rules.planes(states, dtype=torch.int64, backend=self.be)
-                counts = self.ex_counts[rows[0]:rows[-1] + 1, g].to(torch.float64)
-                moves = torch.arange(played, device=self.be.device)
-                temp1 = (moves + 1) < self.temp_threshold
-                pi = counts / counts.sum(dim=1, keepdim=True)
-                acts = self.ex_actions[rows[0]:rows[-1] + 1, g].long()
-                onehot = torch.zeros_like(pi)
-                onehot[moves, acts] = 1.0
-                pi = torch.where(temp1[:, None], pi, onehot)
-                per = 1
-                if expand_symmetries:
-                    planes = rules.symmetries(planes.contiguous(), backend=self.be).reshape(-1, 4, 7, 7)
-                    pi = rules.symmetries(pi.reshape(played, 7, 7, 7).contiguous(), backend=self.be).reshape(-1, 343)
-                    per = 36
-                # side to move of each recorded state vs the side to move at the end
-                movers = np.where(st_all[rows, g]["player"] == 0, 1, -1)
+                movers = np.where(st_all[rows, g]["player"] == 0, 1, -1)   # side to move of each recorded state
                 final = after_all[mv, g]
                 end_player = 1 if final["player"] == 0 else -1
                 result = value_of[int(final["outcome"])]
@@ -230,10 +217,24 @@ class SelfPlayEngine:
                     players = np.repeat(movers, per)
                 else:
                     players = np.concatenate([np.full(per * (i + 1), movers[i]) for i in range(played)])[: per * played]
-                v = np.where(players == end_player, result, -result)
-                out_planes.append(planes.cpu().numpy())
-                out_pi.append(pi.cpu().numpy())
-                out_v.append(v.astype(np.float64))
-        if not out_planes:
+                values.append(np.where(players == end_player, result, -result).astype(np.float64))
+                sel_mv.append(rows)
+                sel_g.append(np.full(played, g))
+        if not sel_mv:
             return np.zeros((0, 4, 7, 7), np.int64), np.zeros((0, 343)), np.zeros(0)
-        return np.concatenate(out_planes), np.concatenate(out_pi), np.concatenate(out_v)
+        mv_idx = torch.from_numpy(np.concatenate(sel_mv)).to(dev)
+        g_idx = torch.from_numpy(np.concatenate(sel_g)).to(dev)
+        # 2. planes, pi and their 36 symmetric forms for ALL selected (move, game) pairs in a handful of kernel calls
+        states = self.ex_states[mv_idx, g_idx].contiguous()
+        planes = rules.planes(states, dtype=torch.int64, backend=self.be)
+        counts = self.ex_counts[mv_idx, g_idx].to(torch.float64)
+        acts = self.ex_actions[mv_idx, g_idx].long()
+        ep_move = torch.from_numpy(np.concatenate([np.arange(len(r)) for r in sel_mv])).to(dev)
+        pi = counts / counts.sum(dim=1, keepdim=True)                                    # MCTS.py:58-60 at temp 1
+        onehot = torch.zeros_like(pi)
+        onehot[torch.arange(len(acts), device=dev), acts] = 1.0                          # MCTS.py:51-56 at temp 0
+        pi = torch.where(((ep_move + 1) < self.temp_threshold)[:, None], pi, onehot)
+        if expand_symmetries:
+            planes = rules.symmetries(planes.contiguous(), backend=self.be).reshape(-1, 4, 7, 7)
+            pi = rules.symmetries(pi.reshape(-1, 7, 7, 7).contiguous(), backend=self.be).reshape(-1, 343)
+        return planes.cpu().numpy(), pi.cpu().numpy(), np.concatenate(values)
