@@ -55,7 +55,8 @@ class MCTS:
         state["tag"] = 0
         if self._tree is None:
             self._tree = BatchedMCTS(1, sims, cpuct, seed=self._seed, backend=self._backend,
-                                     nodes_per_game=min(16383, max(4096, 16 * sims)))
+                                     nodes_per_game=min(16383, max(4096, 16 * sims)),
+                                     terminal_sims_per_wave=0)   # one game: fewest launches, no tail to bound
             self._tree.reset(state)
         else:
             self._tree.set_params(sims, cpuct)

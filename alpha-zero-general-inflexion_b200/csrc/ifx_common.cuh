@@ -28,6 +28,7 @@
   static inline double ifx_dadd(double a, double b) { return a + b; }
   static inline double ifx_ddiv(double a, double b) { return a / b; }
   static inline double ifx_dsqrt(double a) { return sqrt(a); }
+  static inline float ifx_fsqrt(float a) { return sqrtf(a); }
 #else
   #include <cuda_runtime.h>
   #define IFX_HD __device__ __forceinline__
@@ -46,6 +47,7 @@
   IFX_D double ifx_dadd(double a, double b) { return __dadd_rn(a, b); }
   IFX_D double ifx_ddiv(double a, double b) { return __ddiv_rn(a, b); }
   IFX_D double ifx_dsqrt(double a) { return __dsqrt_rn(a); }
+  IFX_D float ifx_fsqrt(float a) { return __fsqrt_rn(a); }
 #endif
 
 #ifdef IFX_HOSTSIM
@@ -70,12 +72,16 @@ static inline float ifx_h2f(uint16_t h) {
   float f; memcpy(&f, &bits, 4); return f;
 }
 static inline float ifx_expf(float x) { return expf(x); }
+static inline float ifx_fast_expf(float x) { return expf(x); }
+static inline float ifx_frcp(float x) { return 1.0f / x; }
 static inline float ifx_logf(float x) { return logf(x); }
 static inline float ifx_tanhf(float x) { return tanhf(x); }
 #else
 #include <cuda_fp16.h>
 IFX_D float ifx_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 IFX_D float ifx_expf(float x) { return expf(x); }
+IFX_D float ifx_fast_expf(float x) { return __expf(x); }        // FMUL + MUFU.EX2 (2 ulp); fused-head path only
+IFX_D float ifx_frcp(float x) { return __frcp_rn(x); }
 IFX_D float ifx_logf(float x) { return logf(x); }
 IFX_D float ifx_tanhf(float x) { return tanhf(x); }
 #endif

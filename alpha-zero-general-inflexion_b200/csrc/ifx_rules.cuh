@@ -88,7 +88,8 @@ IFX_HD double ifx_outcome_value(int outcome) {
 // Source cell of board symmetry `sym` = k + 6*shift + 42*axis for destination cell (r,q):
 // out[r,q] = in[src] where out = translate(rotate(in, k), shift, axis)
 // (InflexionGame.py:115-122, 124-196; index maps verified in SURVEY.md appendix C).
-IFX_HD int ifx_mod7(int x) { x %= IFX_N; return x < 0 ? x + IFX_N : x; }
+// x mod 7 for -14 <= x <= 34 (every caller below): three integer operations instead of a signed remainder
+IFX_HD int ifx_mod7(int x) { x += 14; return x - IFX_N * ((x * 37) >> 8); }
 IFX_HD int ifx_rot_src(int k, int r, int q) {
   const int s = ifx_mod7(r + q);
   int rr, qq;

@@ -57,8 +57,12 @@ IFX_HD uint32_t ifx_n_count(uint32_t raw) { return raw == IFX_N_INVALID ? 0u : (
 struct alignas(16) IfxHead { int32_t ns; float sq_seen, sq_unseen; int32_t pad; };
 IFX_HD IfxHead ifx_head_of(int ns) {
   IfxHead h; h.ns = ns; h.pad = 0;
-  h.sq_seen = (float)ifx_dsqrt((double)ns);                 // float32(math.sqrt(Ns))        MCTS.py:122
-  h.sq_unseen = (float)ifx_dsqrt((double)ns + 1e-8);        // float32(math.sqrt(Ns + EPS))  MCTS.py:125
+  // float32(math.sqrt(Ns)) (MCTS.py:122) and float32(math.sqrt(Ns + 1e-8)) (MCTS.py:125).  For every integer
+  // 1 <= Ns < 2^17 (the width of a visit count) both equal the correctly rounded float32 square root of Ns
+  // (exhaustively checked in tests/test_oracle_mcts.py), so no float64 square root runs on the backup path.
+  const float s = ifx_fsqrt((float)ns);
+  h.sq_seen = s;
+  h.sq_unseen = ns > 0 ? s : 1e-4f;                         // float32(sqrt(1e-8)) = float32(1e-4)
   return h;
 }
 
@@ -73,7 +77,7 @@ struct TreeParams {
   IfxU4* path;          // [G][32]   {slot << 9 | action, N word, Q bits, Ns} per level (valid while a leaf is pending)
   ifx_state* roots;     // [G]
   ifx_state* leaves;    // [G]
-  int32_t G, C, H, maxd, num_sims, logits;
+  int32_t G, C, H, maxd, num_sims, logits, term_budget;
   uint64_t* debug;      // optional [G][8]: ns stamps {start, loads done, expanded, backed up, first level done, end}, depth, probes
   float cpuct;
   uint64_t seed;
@@ -109,14 +113,21 @@ IFX_HD uint32_t tree_valid4(uint64_t own, uint64_t spawn, int a) {
 }
 
 // ---- hash (open addressing, linear probing, never deleted from: rebuilt when nodes are reclaimed) ----
-// returns the slot, or -1; *miss_pos = position of the first empty entry of the probe sequence (insert point)
-IFX_D int tree_hash_find(const TreeParams& P, int g, uint64_t k0, uint64_t k1, int* miss_pos) {
+// The first group of 32 entries is requested by tree_hash_issue; the caller may do unrelated work before
+// tree_hash_resolve consumes it (and keeps probing in the rare case the first group decides nothing).
+// resolve returns the slot, or -1 with *miss_pos = position of the first empty entry of the probe sequence
+// (the insert point).
+IFX_D void tree_hash_issue(const TreeParams& P, int g, uint32_t h, LaneVar<IfxKey>& first) {
   const IfxKey* tab = P.hash + (int64_t)g * P.H;
-  const uint32_t h = ifx_hash_key(k0, k1);
+  IFX_FOR_LANES(l) { first[l] = tab[(h + l) & (P.H - 1)]; }
+}
+IFX_D int tree_hash_resolve(const TreeParams& P, int g, uint64_t k0, uint64_t k1, uint32_t h, const LaneVar<IfxKey>& first,
+                            int* miss_pos) {
+  const IfxKey* tab = P.hash + (int64_t)g * P.H;
   for (int probe = 0; probe < P.H; probe += 32) {
     LaneVar<int> match, empty, slot;
     IFX_FOR_LANES(l) {
-      const IfxKey e = tab[(h + probe + l) & (P.H - 1)];
+      const IfxKey e = probe == 0 ? first[l] : tab[(h + probe + l) & (P.H - 1)];
       match[l] = (e.k0 == k0 && (e.k1 & IFX_KEY1_MASK) == k1) ? 1 : 0;
       empty[l] = e.k0 == IFX_KEY_EMPTY ? 1 : 0;
       slot[l] = (int)(e.k1 >> 50);
@@ -129,11 +140,40 @@ IFX_D int tree_hash_find(const TreeParams& P, int g, uint64_t k0, uint64_t k1, i
   return -1;
 }
 
+// ---- the root's rows, mirrored in shared memory for the length of a wave ----
+// Every simulation starts at the root, and the root slot is known as soon as the game record has arrived, i.e.
+// long before the pending leaf has been expanded and backed up.  Its three rows, header and key are therefore
+// copied into shared memory with cp.async right away (no registers held, the copy flies under the expansion),
+// the backup patches the one edge it changes, and every simulation of the wave selects from the mirror: one
+// HBM read of the root per wave and no dependent round trip at the start of a simulation.
+struct alignas(16) RootMirror { float rows[3 * IFX_ROW]; IfxHead head; IfxKey key; };
+
+#ifdef IFX_HOSTSIM
+static inline void ifx_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+static inline void ifx_cp_async_wait() {}
+#else
+IFX_D void ifx_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+IFX_D void ifx_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
+IFX_D void tree_mirror_fetch(const TreeParams& P, int g, int slot, RootMirror* M) {
+  const char* src = reinterpret_cast<const char*>(tree_row(P, g, slot, 0));
+  char* dst = reinterpret_cast<char*>(M->rows);
+  IFX_FOR_LANES(l) {
+    for (int i = l; i < 3 * IFX_ROW / 4; i += 32) ifx_cp_async16(dst + 16 * i, src + 16 * i);
+    if (l == 0) ifx_cp_async16(&M->head, &P.node_head[(int64_t)g * P.C + slot]);
+    if (l == 1) ifx_cp_async16(&M->key, &P.node_key[(int64_t)g * P.C + slot]);
+  }
+}
+IFX_D void tree_mirror_wait() { ifx_cp_async_wait(); IFX_SYNCWARP(); }
+
 // ---- one edge of the backup (MCTS.py:136-142 under NEP-50 promotion) ----
 // (raw N, Q32) were loaded ahead of time; q64 is touched only for Python-float edges.  `child` (>= 0) refreshes
-// the edge's child hint.
+// the edge's child hint.  `mirror` (nullable) receives the same N and Q words (the edge belongs to the root).
 IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, uint32_t raw, float q32, double v, bool v_is32,
-                             int child) {
+                             int child, RootMirror* mirror) {
   uint32_t* nrow = reinterpret_cast<uint32_t*>(tree_row(P, g, slot, 1));
   float* qrow = tree_row(P, g, slot, 2);
   double* q64 = P.q64 + ((int64_t)g * P.C + slot) * 344 + a;
@@ -141,21 +181,28 @@ IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, uint32
   const bool q_is64 = (raw & IFX_N_TAG) != 0;
   const uint32_t hint = child >= 0 ? ((uint32_t)child << IFX_N_HINT_SHIFT) : (raw & (IFX_N_HINT_NONE << IFX_N_HINT_SHIFT));
   bool new_is64;
+  float qnew;
   if (n == 0) {                                    // first visit: Q = v, same kind
     new_is64 = !v_is32;
     if (new_is64) *q64 = v;
-    qrow[a] = (float)v;
+    qnew = (float)v;
   } else if (q_is64 && !v_is32) {                  // Python float with Python float: float64 throughout
     const double q = ifx_ddiv(ifx_dadd(ifx_dmul((double)n, *q64), v), (double)(n + 1));
-    *q64 = q; qrow[a] = (float)q; new_is64 = true;
+    *q64 = q; qnew = (float)q; new_is64 = true;
   } else if (!q_is64) {                            // float32 Q: everything rounds to float32
-    qrow[a] = ifx_fdiv(ifx_fadd(ifx_fmul((float)n, q32), (float)v), (float)(n + 1));
+    qnew = ifx_fdiv(ifx_fadd(ifx_fmul((float)n, q32), (float)v), (float)(n + 1));
     new_is64 = false;
   } else {                                         // Python-float Q meets a float32 value: N*Q in float64, then float32
-    qrow[a] = ifx_fdiv(ifx_fadd((float)ifx_dmul((double)n, *q64), (float)v), (float)(n + 1));
+    qnew = ifx_fdiv(ifx_fadd((float)ifx_dmul((double)n, *q64), (float)v), (float)(n + 1));
     new_is64 = false;
   }
-  nrow[a] = (n + 1) | hint | (new_is64 ? IFX_N_TAG : 0u);
+  const uint32_t nnew = (n + 1) | hint | (new_is64 ? IFX_N_TAG : 0u);
+  qrow[a] = qnew;
+  nrow[a] = nnew;
+  if (mirror) {
+    mirror->rows[2 * IFX_ROW + a] = qnew;
+    reinterpret_cast<uint32_t*>(mirror->rows)[IFX_ROW + a] = nnew;
+  }
 }
 
 // The path lives one level per lane (lane L holds edge L) as {slot << 9 | action, N word, Q bits, Ns}: the
@@ -163,9 +210,9 @@ IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, uint32
 // before its backup, so the backup needs no loads of its own.
 // Back `v` (the value returned by the deepest search() call) up the first `depth` edges of the path; levels
 // are independent: distinct nodes (the turn strictly grows along a path).  `leaf_slot` is the node the last
-// edge leads to (-1: terminal state, no node).
+// edge leads to (-1: terminal state, no node).  Level 0 is the root: `mirror` (nullable) is kept in step.
 IFX_D void tree_backup_apply(const TreeParams& P, int g, int depth, const LaneVar<IfxU4>& path, double v, bool v_is32,
-                             int leaf_slot) {
+                             int leaf_slot, RootMirror* mirror) {
   LaneVar<uint32_t> edge, below;
   IFX_FOR_LANES(l) { edge[l] = path[l].x; }
   lanes_shift_down(edge, below);                            // path entry one level deeper
@@ -174,8 +221,11 @@ IFX_D void tree_backup_apply(const TreeParams& P, int g, int depth, const LaneVa
       const int slot = (int)(edge[l] >> 9), a = (int)(edge[l] & 511u);
       const double vl = ((depth - 1 - l) & 1) ? -v : v;     // each level returns -v to its parent (MCTS.py:145)
       const int child = l + 1 < depth ? (int)(below[l] >> 9) : leaf_slot;
-      tree_update_edge(P, g, slot, a, path[l].y, ifx_u2f(path[l].z), vl, v_is32, child);
-      P.node_head[(int64_t)g * P.C + slot] = ifx_head_of((int)path[l].w + 1);               // MCTS.py:144
+      RootMirror* mr = l == 0 ? mirror : nullptr;
+      tree_update_edge(P, g, slot, a, path[l].y, ifx_u2f(path[l].z), vl, v_is32, child, mr);
+      const IfxHead hd = ifx_head_of((int)path[l].w + 1);   // MCTS.py:144
+      P.node_head[(int64_t)g * P.C + slot] = hd;
+      if (mr) mr->head = hd;
     }
   }
   IFX_SYNCWARP();
@@ -211,6 +261,30 @@ IFX_D void tree_rows_load(const TreeParams& P, int g, int slot, RowRegs& R) {
   }
   R.head = P.node_head[(int64_t)g * P.C + slot];
   R.key = P.node_key[(int64_t)g * P.C + slot];
+}
+
+IFX_D void tree_rows_from_mirror(const RootMirror* M, RowRegs& R) {
+  const float* prow = M->rows; const float* nrow = M->rows + IFX_ROW; const float* qrow = M->rows + 2 * IFX_ROW;
+  IFX_FOR_LANES(l) {
+    const int i = 4 * l;
+    R.p0[l] = *reinterpret_cast<const IfxF4*>(prow + i);
+    R.n0[l] = *reinterpret_cast<const IfxU4*>(nrow + i);
+    R.q0[l] = *reinterpret_cast<const IfxF4*>(qrow + i);
+    R.p1[l] = *reinterpret_cast<const IfxF4*>(prow + i + 128);
+    R.n1[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 128);
+    R.q1[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 128);
+    if (i + 256 < IFX_ROW) {
+      R.p2[l] = *reinterpret_cast<const IfxF4*>(prow + i + 256);
+      R.n2[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 256);
+      R.q2[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 256);
+    } else {
+      const IfxF4 zf = {0.f, 0.f, 0.f, 0.f};
+      const IfxU4 zu = {IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID};
+      R.p2[l] = zf; R.q2[l] = zf; R.n2[l] = zu;
+    }
+  }
+  R.head = M->head;
+  R.key = M->key;
 }
 
 IFX_D int tree_select(const TreeParams& P, const RowRegs& R, uint32_t* chosen_raw, float* chosen_q) {
@@ -297,10 +371,13 @@ IFX_D void tree_policy_load(const float* pi, bool aligned, PolicyRegs& R) {
 }
 
 // Fused head mode (policy_is_logits = 2): `head` is the net's last GEMM output for this game, binary16
-// [>= 344]: 343 policy logits + the value pre-activation.  Computes exp(log_softmax(logits)) (NNet.py:94 with
-// InflexionNNet.py:54) and tanh(value) here, so no elementwise kernel runs between the GEMM and the tree.
-IFX_D float tree_head_softmax(const uint16_t* head, PolicyRegs& R) {
-  LaneVar<float> lmax, lsum;
+// [>= 344]: 343 policy logits + the value pre-activation.  The reference computes exp(log_softmax(logits))
+// (NNet.py:94 with InflexionNNet.py:54), masks it and renormalises over the valid moves (MCTS.py:95-97); the
+// softmax denominator cancels in that renormalisation, so this returns only e_i = exp(logit_i - max) and
+// tree_expand divides by the sum over the VALID moves.  Also returns tanh(value).  No elementwise kernel runs
+// between the GEMM and the tree.  (float32 throughout; agreement with the fp32 module is a tolerance, 1e-3.)
+IFX_D float tree_head_exp(const uint16_t* head, PolicyRegs& R) {
+  LaneVar<float> lmax;
   IFX_FOR_LANES(l) {
     float mx = -INFINITY;
 #pragma unroll
@@ -319,20 +396,6 @@ IFX_D float tree_head_softmax(const uint16_t* head, PolicyRegs& R) {
     lmax[l] = mx;
   }
   const float m = lanes_max_f32(lmax);
-  float value = 0.0f;
-  IFX_FOR_LANES(l) {
-    float sm = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int i = 4 * l + 128 * j;
-      IfxF4 v = R.p[j][l];
-      v.x = i < IFX_ACTIONS ? ifx_expf(v.x - m) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_expf(v.y - m) : 0.0f;
-      v.z = i + 2 < IFX_ACTIONS ? ifx_expf(v.z - m) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_expf(v.w - m) : 0.0f;
-      sm += (v.x + v.y) + (v.z + v.w);
-    }
-    lsum[l] = sm;
-  }
-  const float lse = ifx_logf(lanes_sum_f32(lsum));
   LaneVar<float> val;
   IFX_FOR_LANES(l) {
     val[l] = 0.0f;
@@ -341,18 +404,18 @@ IFX_D float tree_head_softmax(const uint16_t* head, PolicyRegs& R) {
       const int i = 4 * l + 128 * j;
       IfxF4 v = R.p[j][l];
       if (i == 340) val[l] = ifx_tanhf(v.w);                                // lane 21, j = 2 holds element 343
-      v.x = i < IFX_ACTIONS ? ifx_expf((v.x - m) - lse) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_expf((v.y - m) - lse) : 0.0f;
-      v.z = i + 2 < IFX_ACTIONS ? ifx_expf((v.z - m) - lse) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_expf((v.w - m) - lse) : 0.0f;
+      v.x = i < IFX_ACTIONS ? ifx_fast_expf(v.x - m) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_fast_expf(v.y - m) : 0.0f;
+      v.z = i + 2 < IFX_ACTIONS ? ifx_fast_expf(v.z - m) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_fast_expf(v.w - m) : 0.0f;
       R.p[j][l] = v;
     }
   }
-  value = lanes_bcast(val, 21);
-  return value;
+  return lanes_bcast(val, 21);
 }
 
 // ---- expansion of the pending leaf (MCTS.py:89-112) ----
 // returns the slot, or -1 with a fault bit set
-IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, const PolicyRegs& R, float* buf) {
+IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, const PolicyRegs& R, float* buf,
+                      const bool fused) {
   const uint64_t own = ifx_own(leaf), spawn = ifx_spawn_mask(leaf);
   LaneVar<uint32_t> vbits;                                  // validity of the lane's 12 actions (4 bits per group)
   LaneVar<IfxF4> m0, m1, m2;                                // policies *= valids (MCTS.py:95)
@@ -368,14 +431,25 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
       v.x = (b & 1u) ? v.x : 0.0f; v.y = (b & 2u) ? v.y : 0.0f;
       v.z = (b & 4u) ? v.z : 0.0f; v.w = (b & 8u) ? v.w : 0.0f;
       mv[j] = v;
-      if (i < IFX_ROW) *reinterpret_cast<IfxF4*>(buf + i) = v;
+      if (!fused && i < IFX_ROW) *reinterpret_cast<IfxF4*>(buf + i) = v;
     }
     vbits[l] = vb; m0[l] = mv[0]; m1[l] = mv[1]; m2[l] = mv[2];
   }
-  IFX_SYNCWARP();
-  float total = tree_pairwise_sum343(buf);                  // policies.sum()
+  float total;
+  if (fused) {                                              // float32 net output: any summation order is within tolerance
+    LaneVar<float> part;
+    IFX_FOR_LANES(l) {
+      part[l] = ((m0[l].x + m0[l].y) + (m0[l].z + m0[l].w)) + ((m1[l].x + m1[l].y) + (m1[l].z + m1[l].w)) +
+                ((m2[l].x + m2[l].y) + (m2[l].z + m2[l].w));
+    }
+    total = lanes_sum_f32(part);
+  } else {
+    IFX_SYNCWARP();
+    total = tree_pairwise_sum343(buf);                      // policies.sum(), numpy's order
+  }
   const bool uniform = !(total > 0.0f);                     // MCTS.py:98-107: all valid moves masked
   if (uniform) total = (float)ifx_num_valid(leaf);          // sum of 0/1 values is exact in any order
+  const float inv_total = fused ? ifx_frcp(total) : 0.0f;
   const int slot = G.next_slot;
   if (slot < 0) { G.faults |= IFX_F_POOL; return -1; }
   if (G.leaf_hpos < 0) { G.faults |= IFX_F_HASH; return -1; }
@@ -397,9 +471,13 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
         }
         // policies /= sum.  Invalid entries are exactly 0 either way; dividing a dummy 1.0 for them keeps the
         // zero numerators out of the IEEE division's slow path (which the whole warp would otherwise take).
-        const float qx = ifx_fdiv((b & 1u) ? v.x : 1.0f, total), qy = ifx_fdiv((b & 2u) ? v.y : 1.0f, total);
-        const float qz = ifx_fdiv((b & 4u) ? v.z : 1.0f, total), qw = ifx_fdiv((b & 8u) ? v.w : 1.0f, total);
-        v.x = (b & 1u) ? qx : 0.0f; v.y = (b & 2u) ? qy : 0.0f; v.z = (b & 4u) ? qz : 0.0f; v.w = (b & 8u) ? qw : 0.0f;
+        if (fused) {                                        // one reciprocal, twelve multiplies (masked entries stay 0)
+          v.x *= inv_total; v.y *= inv_total; v.z *= inv_total; v.w *= inv_total;
+        } else {
+          const float qx = ifx_fdiv((b & 1u) ? v.x : 1.0f, total), qy = ifx_fdiv((b & 2u) ? v.y : 1.0f, total);
+          const float qz = ifx_fdiv((b & 4u) ? v.z : 1.0f, total), qw = ifx_fdiv((b & 8u) ? v.w : 1.0f, total);
+          v.x = (b & 1u) ? qx : 0.0f; v.y = (b & 2u) ? qy : 0.0f; v.z = (b & 4u) ? qz : 0.0f; v.w = (b & 8u) ? qw : 0.0f;
+        }
         *reinterpret_cast<IfxF4*>(prow + i) = v;
         IfxU4 z;                                             // Vs[s] folded into the N row (MCTS.py:109)
         z.x = (b & 1u) ? IFX_N_FRESH : IFX_N_INVALID; z.y = (b & 2u) ? IFX_N_FRESH : IFX_N_INVALID;
@@ -424,10 +502,14 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
   return slot;
 }
 
-// planes of `st` under the random symmetry drawn for (game, move, sim) -> float32 [4][49] (MCTS.py:90-92)
-IFX_D void tree_write_nn_input(const TreeParams& P, const IfxGame& G, const ifx_state& st, float* out) {
+// random_symmetry of (game, move, sim): k + 6*shift + 42*axis (InflexionGame.py:115-122; MCTS.py:90-92)
+IFX_D int tree_draw_symmetry(const TreeParams& P, const IfxGame& G) {
   const IfxRand4 r = ifx_philox(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)G.sims_done, IFX_RNG_SYMMETRY);
-  const int sym = (int)(r.w[0] % 6u) + 6 * (int)(r.w[1] % 7u) + 42 * (int)(r.w[2] % 3u);
+  return (int)(r.w[0] % 6u) + 6 * (int)(r.w[1] % 7u) + 42 * (int)(r.w[2] % 3u);
+}
+
+// planes of `st` under symmetry `sym` -> float32 [4][49] (the net's input row of this game)
+IFX_D void tree_write_nn_input(const ifx_state& st, int sym, float* out) {
   const uint64_t own = ifx_own(st), opp = ifx_opp(st);
   const float turn = (float)st.turn, spawn = ifx_can_spawn(st) ? 1.0f : 0.0f;
   IFX_FOR_LANES(l) {
@@ -448,20 +530,24 @@ static inline uint64_t ifx_now_ns() { return 0; }
 IFX_D uint64_t ifx_now_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
+template <bool DBG>
 IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_t pi_stride, const float* nn_v,
-                          float* nn_in, float* buf) {
-  const uint64_t dbg_t0 = P.debug ? ifx_now_ns() : 0;
+                          float* nn_in, float* buf, RootMirror* mirror) {
+  const uint64_t dbg_t0 = DBG ? ifx_now_ns() : 0;
   uint64_t dbg_t1 = 0, dbg_t2 = 0, dbg_t3 = 0, dbg_t4 = 0;
   int dbg_depth = 0, dbg_probes = 0;
   // round trip 1: everything whose address is known up front, issued together (leaf / policy / value are
   // speculative: they are only used when a leaf is pending, which is the common case)
   IfxGame G = P.games[g];
+  // the root's rows start moving into shared memory the moment the record is here; they land while the pending
+  // leaf is expanded and backed up
+  int mirror_slot = G.root_slot;
+  if (mirror_slot >= 0) tree_mirror_fetch(P, g, mirror_slot, mirror);
   const ifx_state leaf = P.leaves[g];
-  const ifx_state root = P.roots[g];                         // does not change within a wave
   float leaf_v;
   PolicyRegs pol;
-  if (P.logits == 2) {                                      // binary16 head output: softmax + tanh fused here
-    leaf_v = tree_head_softmax(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g * pi_stride, pol);
+  if (P.logits == 2) {                                      // binary16 head output: exp + tanh fused here
+    leaf_v = tree_head_exp(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g * pi_stride, pol);
   } else {
     leaf_v = nn_v[g];
     const float* pi_row = nn_pi + (int64_t)g * pi_stride;
@@ -469,32 +555,44 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   }
   LaneVar<IfxU4> path;
   IFX_FOR_LANES(l) { path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
-  if (G.faults) return;
-  if (P.debug) dbg_t1 = ifx_now_ns() + (uint64_t)(G.pending & 0) + (uint64_t)(leaf.turn & 0);
+  if (G.faults) { if (mirror_slot >= 0) tree_mirror_wait(); return; }
+  if (DBG) dbg_t1 = ifx_now_ns() + (uint64_t)(G.pending & 0) + (uint64_t)(leaf.turn & 0);
   if (G.pending) {
-    const int slot = tree_expand(P, g, G, leaf, pol, buf);
-    if (P.debug) dbg_t2 = ifx_now_ns();
+    const int slot = tree_expand(P, g, G, leaf, pol, buf, P.logits == 2);
+    if (DBG) dbg_t2 = ifx_now_ns();
+    if (mirror_slot >= 0) tree_mirror_wait();               // the backup patches the mirror: it must have landed
     if (slot >= 0) {
       if (G.path_len == 0) G.root_slot = slot;              // the root itself was the leaf
       // search() of the leaf returns -v, v a float32 (MCTS.py:112; NNet.py:94)
-      tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot);
+      tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot, mirror_slot >= 0 ? mirror : nullptr);
       G.sims_done += 1; G.n_sims += 1;
     }
     G.pending = 0;
-    if (P.debug) dbg_t3 = ifx_now_ns();
+    if (DBG) dbg_t3 = ifx_now_ns();
+  } else if (mirror_slot >= 0) {
+    tree_mirror_wait();
   }
-  while (!G.faults && G.sims_done < P.num_sims) {
-    ifx_state st = root;
-    int depth = 0;
+  int term_left = P.term_budget > 0 ? P.term_budget : 0x7fffffff;
+  while (!G.faults && G.sims_done < P.num_sims && term_left > 0) {
+    ifx_state st = P.roots[g];                              // re-read per simulation (an L1/L2 hit) instead of sixteen
+    int depth = 0;                                          // registers held across the whole wave
     int slot = G.root_slot;                                 // -1: the root is not expanded yet
     bool verified = slot >= 0;                              // the cached root slot needs no key check
     RowRegs rows;
     bool inflight = slot >= 0;
-    if (inflight) tree_rows_load(P, g, slot, rows);         // root rows: issued before anything else of this simulation
+    if (inflight) {
+      if (mirror_slot != slot) {                            // the root was expanded in this very wave (once per move at most)
+        tree_mirror_fetch(P, g, slot, mirror);
+        tree_mirror_wait();
+        mirror_slot = slot;
+      }
+      tree_rows_from_mirror(mirror, rows);
+    }
     for (;;) {
       if (st.outcome != IFX_ONGOING) {                      // MCTS.py:85-87: terminal, value is a Python number
-        tree_backup_apply(P, g, depth, path, -ifx_outcome_value(st.outcome), false, -1);
+        tree_backup_apply(P, g, depth, path, -ifx_outcome_value(st.outcome), false, -1, mirror_slot >= 0 ? mirror : nullptr);
         G.sims_done += 1; G.n_sims += 1; G.n_term += 1;
+        term_left -= 1;
         break;
       }
       const uint64_t k0 = ifx_key0(st), k1 = ifx_key1(st);
@@ -503,16 +601,23 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
       // whether the hint was right (the reference looks nodes up by planes, not by edge: SURVEY.md H1)
       if (inflight && !verified && !(rows.key.k0 == k0 && rows.key.k1 == k1)) slot = -1;
       if (slot < 0) {
-        slot = tree_hash_find(P, g, k0, k1, &miss_pos);
-        dbg_probes += 1;
-        if (slot >= 0) tree_rows_load(P, g, slot, rows);
-      }
-      if (slot < 0) {                                       // MCTS.py:89: leaf -> wait for the net
-        if (IFX_LANE0) P.leaves[g] = st;
-        IFX_FOR_LANES(l) { if (l < depth) P.path[(int64_t)g * IFX_MAX_DEPTH + l] = path[l]; }
-        tree_write_nn_input(P, G, st, nn_in + (int64_t)g * 196);
-        G.path_len = depth; G.pending = 1; G.leaf_hpos = miss_pos;
-        break;
+        // look the state up by key; the symmetry this simulation would feed the net with is drawn (Philox, ~100
+        // instructions) while the probe is in flight
+        const uint32_t h = ifx_hash_key(k0, k1);
+        LaneVar<IfxKey> first;
+        tree_hash_issue(P, g, h, first);
+        const int sym = tree_draw_symmetry(P, G);
+        slot = tree_hash_resolve(P, g, k0, k1, h, first, &miss_pos);
+        if (DBG) dbg_probes += 1;
+        if (slot >= 0) {
+          tree_rows_load(P, g, slot, rows);
+        } else {                                            // MCTS.py:89: leaf -> wait for the net
+          if (IFX_LANE0) P.leaves[g] = st;
+          IFX_FOR_LANES(l) { if (l < depth) P.path[(int64_t)g * IFX_MAX_DEPTH + l] = path[l]; }
+          tree_write_nn_input(st, sym, nn_in + (int64_t)g * 196);
+          G.path_len = depth; G.pending = 1; G.leaf_hpos = miss_pos;
+          break;
+        }
       }
       G.n_visits += 1;
       uint32_t raw = 0; float qsel = 0.0f;
@@ -526,8 +631,8 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
         }
       }
       depth += 1;
-      if (P.debug && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
-      dbg_depth = depth > dbg_depth ? depth : dbg_depth;
+      if (DBG && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
+      if (DBG) dbg_depth = depth > dbg_depth ? depth : dbg_depth;
       // request the hinted child's rows BEFORE stepping the board: the loads fly while the rules run
       const uint32_t hint = (raw >> IFX_N_HINT_SHIFT) & IFX_N_HINT_NONE;
       slot = (hint != IFX_N_HINT_NONE && (int)hint < P.C) ? (int)hint : -1;
@@ -539,7 +644,7 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
     if (G.pending) break;
   }
   if (IFX_LANE0) P.games[g] = G;
-  if (P.debug && IFX_LANE0) {
+  if (DBG && IFX_LANE0) {
     uint64_t* d = P.debug + (int64_t)g * 8;
     d[0] = dbg_t0; d[1] = dbg_t1; d[2] = dbg_t2; d[3] = dbg_t3; d[4] = dbg_t4; d[5] = ifx_now_ns();
     d[6] = (uint64_t)dbg_depth; d[7] = (uint64_t)dbg_probes;

@@ -28,6 +28,7 @@ static int check_cfg(const ifx_mcts_config* c) {
   if (c->hash_per_game < 2 * c->nodes_per_game) return IFX_E_ARG;
   if (c->max_depth < 1 || c->max_depth > IFX_MAX_DEPTH || c->num_sims < 0) return IFX_E_ARG;
   if (c->policy_is_logits != 0 && c->policy_is_logits != 2) return IFX_E_ARG;
+  if (c->terminal_sims_per_wave < 0) return IFX_E_ARG;
   return IFX_OK;
 }
 
@@ -126,12 +127,14 @@ IFX_D void body_status(const TreeParams& P, int g, int32_t* status) {
 #define IFX_WAVE_MIN_BLOCKS 20     // resident CTAs per SM the wave kernel is compiled for (register cap 65536/(32*n))
 #endif
 
+template <bool DBG>
 __global__ void __launch_bounds__(TREE_BLOCK, IFX_WAVE_MIN_BLOCKS)
 tree_wave_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_stride, const float* __restrict__ nn_v,
                  float* __restrict__ nn_in) {
   __shared__ float buf[TREE_WARPS][IFX_ROW];
+  __shared__ RootMirror mirror[TREE_WARPS];
   const int w = threadIdx.x >> 5, g = blockIdx.x * TREE_WARPS + w;
-  if (g < P.G) tree_wave_game(P, g, nn_pi, pi_stride, nn_v, nn_in, buf[w]);
+  if (g < P.G) tree_wave_game<DBG>(P, g, nn_pi, pi_stride, nn_v, nn_in, buf[w], &mirror[w]);
 }
 
 __global__ void __launch_bounds__(TREE_BLOCK)
@@ -234,8 +237,14 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   P.free_stack = (uint16_t*)(b + L.free_stack); P.games = (IfxGame*)(b + L.per_game);
   P.path = (IfxU4*)(b + L.path); P.roots = (ifx_state*)(b + L.roots); P.leaves = (ifx_state*)(b + L.leaves);
   P.G = c->n_games; P.C = c->nodes_per_game; P.H = c->hash_per_game; P.maxd = c->max_depth;
-  P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.cpuct = c->cpuct; P.seed = c->seed;
+  P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.term_budget = c->terminal_sims_per_wave; P.cpuct = c->cpuct; P.seed = c->seed;
   P.debug = nullptr;
+#ifndef IFX_HOSTSIM
+  // one warp per CTA, ~6 KB of shared memory each: ask for the largest shared-memory carve-out so that the
+  // register-limited number of CTAs per SM (IFX_WAVE_MIN_BLOCKS) is also what shared memory allows
+  cudaFuncSetAttribute(tree_wave_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(tree_wave_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
   *out = m;
   return IFX_OK;
 }
@@ -313,7 +322,8 @@ int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const floa
   } else if (!nn_v) return IFX_E_ARG;
 #ifdef IFX_HOSTSIM
   float buf[IFX_ROW];
-  for (int g = 0; g < m->P.G; ++g) tree_wave_game(m->P, g, nn_pi, pi_stride, nn_v, nn_in, buf);
+  static RootMirror mirror;
+  for (int g = 0; g < m->P.G; ++g) tree_wave_game<false>(m->P, g, nn_pi, pi_stride, nn_v, nn_in, buf, &mirror);
   return ifx_after_launch();
 #else
   const bool timed = m->timing && m->n_timed < IFX_TIMING_RING;
@@ -324,7 +334,10 @@ int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const floa
     }
     cudaEventRecord(m->ev[m->n_timed][0], (cudaStream_t)stream);
   }
-  tree_wave_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
+  if (m->P.debug)    // per-warp %globaltimer stamps (tools/trace_wave.py): a separate instantiation, so the product kernel carries none of it
+    tree_wave_kernel<true><<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
+  else
+    tree_wave_kernel<false><<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
   if (timed) { cudaEventRecord(m->ev[m->n_timed][1], (cudaStream_t)stream); m->n_timed += 1; }
   return ifx_after_launch();
 #endif

@@ -32,9 +32,11 @@ def default_pool_size(num_sims: int) -> int:
 class BatchedMCTS:
     def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | None = None,
                  max_depth: int = 32, backend: Backend | None = None, fused_head: bool = False,
-                 pad_policy_rows: bool = True):
+                 pad_policy_rows: bool = True, terminal_sims_per_wave: int = 1):
         """fused_head: the net hands over its last GEMM output (float16 [G,344]: 343 policy logits + the value
-        pre-activation, buffer ``nn_head``) and the tree kernel applies softmax / tanh itself."""
+        pre-activation, buffer ``nn_head``) and the tree kernel applies softmax / tanh itself.
+        terminal_sims_per_wave: how many simulations that end in a terminal state (no net needed) a game may run in
+        one wave before it yields (0 = no limit); results do not depend on it, the length of a wave's tail does."""
         self.be = backend or default_backend()
         self.n_games, self.num_sims = int(n_games), int(num_sims)
         nodes = int(nodes_per_game or default_pool_size(num_sims))
@@ -44,7 +46,8 @@ class BatchedMCTS:
         # float32(cpuct): the reference multiplies a Python number into a float32 (NEP-50 weak scalar, MCTS.py:122)
         self.cfg = _capi.MctsConfig(n_games=self.n_games, nodes_per_game=nodes, hash_per_game=hash_slots,
                                     max_depth=max_depth, num_sims=self.num_sims, cpuct=float(np.float32(cpuct)),
-                                    seed=int(seed) & (2 ** 64 - 1), policy_is_logits=2 if fused_head else 0, reserved=0)
+                                    seed=int(seed) & (2 ** 64 - 1), policy_is_logits=2 if fused_head else 0,
+                                    terminal_sims_per_wave=int(terminal_sims_per_wave))
         dll = self.be.dll
         self.layout = _capi.MctsLayout()
         self.be.check(dll.ifx_mcts_get_layout(C.byref(self.cfg), C.byref(self.layout)))
@@ -134,9 +137,11 @@ class BatchedMCTS:
         as the reference calls ``predict``.  Used by the object-per-game drop-in, where a call is expensive."""
         while True:
             self.wave()
-            if not bool(self.status()[:, 1].any()):
+            st = self.status()
+            if bool(((st[:, 0] >= self.num_sims) | (st[:, 2] != 0)).all()):
                 return
-            self.feed(evaluate)
+            if bool(st[:, 1].any()):                         # (a game that yielded on its terminal budget needs no net)
+                self.feed(evaluate)
 
     def wave_timing(self, enable: bool) -> None:
         """Bracket every (un-captured) wave launch with CUDA events inside the library call (see ifx_mcts_wave_timing)."""

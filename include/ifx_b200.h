@@ -132,7 +132,11 @@ typedef struct ifx_mcts_config {
                                2: nn_pi points at the net's last GEMM output, binary16 rows of pi_stride
                                   (>= 344, multiple of 4) halfs = 343 policy logits + the value pre-activation;
                                   softmax and tanh are fused into the expansion, nn_v is ignored           */
-  int32_t reserved;
+  int32_t terminal_sims_per_wave; /* 0: no limit.  T >= 1: after T simulations that ended in a terminal state
+                               (no net needed, MCTS.py:85-87) the game yields until the next wave.  A game whose best
+                               child is a won position would otherwise run ALL its remaining simulations inside one
+                               launch while the other warps have long finished (the tail of the wave).  Results do
+                               not depend on T; num_sims+1 waves still complete a move (see ifx_mcts_wave)            */
 } ifx_mcts_config;
 
 typedef struct ifx_mcts ifx_mcts;
@@ -187,7 +191,9 @@ IFX_API int ifx_mcts_set_roots(ifx_mcts* m, const ifx_state* roots, void* stream
  *      (MCTS.py:85-87) -- until a simulation reaches an unexpanded state or num_sims are done;
  *   3. the unexpanded state's planes, under the random symmetry of MCTS.py:91-92, are written to
  *      nn_in[g] as float32 [4][7][7] and the game waits for the net.
- * A move needs at most num_sims net evaluations, i.e. num_sims+1 calls of this function. */
+ * A move needs at most num_sims net evaluations, i.e. num_sims+1 calls of this function (also with
+ * terminal_sims_per_wave = T >= 1: after wave w, simulations done + leaf pending >= w+1, because a game yields only
+ * after a leaf went to the net or after at least one terminal simulation of that wave). */
 IFX_API int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const float* nn_v, float* nn_in,
                           void* stream);
 

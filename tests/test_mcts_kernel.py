@@ -205,3 +205,30 @@ def test_dense_policy_rows_give_the_same_search(backend):
     assert m.nn_pi.stride(0) == 343
     for k in ("counts", "q32", "ns"):
         assert torch.equal(out[0][k].cpu(), out[1][k].cpu())
+
+
+def test_terminal_budget_does_not_change_the_search(backend):
+    """terminal_sims_per_wave only decides in which wave a simulation runs: with games that end after 4-6 moves
+    (most simulations reach a terminal state) num_sims+1 waves still complete every move, with identical tables."""
+    G, sims, moves = 5, 24, 5
+    max_turns = np.array([4, 5, 6, 343, 5])
+    ref = None
+    for budget in (0, 1, 2):
+        m = BatchedMCTS(G, sims, 1.0, seed=21, backend=backend, terminal_sims_per_wave=budget)
+        m.reset(start_states(G, max_turns, tags=np.arange(G)))
+        out = []
+        for _ in range(moves):
+            m.search(stub_eval("float"))
+            m.raise_on_faults()
+            st = m.status().cpu().numpy()
+            over = st[:, 4] != 0
+            assert np.all((st[:, 0] == sims) | over) and not st[:, 1].any()
+            stats = m.root_stats(want_q=True)
+            acts = m.sample_actions(2)
+            out.append((stats["counts"].cpu().numpy().copy(), stats["q32"].cpu().numpy().copy(), acts.cpu().numpy().copy()))
+            m.advance(acts)
+        if ref is None:
+            ref = out
+        else:
+            for (c0, q0, a0), (c1, q1, a1) in zip(ref, out):
+                assert np.array_equal(c0, c1) and q0.tobytes() == q1.tobytes() and np.array_equal(a0, a1)

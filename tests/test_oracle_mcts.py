@@ -79,3 +79,14 @@ def test_ndarray_sum_and_handwritten_sum_agree_in_search(golden_dir):
     draws = PhiloxDraws(int(g["seed"]))
     for i, rec in enumerate(self_play_moves(stub_predict("float"), 25, 1, draws, max_moves=6, exact_sum=False)):
         assert np.array_equal(rec["counts"], g["counts"][i])
+
+
+def test_float32_sqrt_identity_behind_the_node_header():
+    """csrc/ifx_tree.cuh:ifx_head_of computes both PUCT square roots (MCTS.py:122,125) as ONE float32 square root.
+    Valid iff, for every visit count the 17-bit N field can hold, float32(math.sqrt(Ns)) and
+    float32(math.sqrt(Ns + 1e-8)) equal the correctly rounded float32 square root of Ns."""
+    n = np.arange(0, 1 << 17, dtype=np.int64)
+    f32 = np.sqrt(n.astype(np.float32))
+    assert np.array_equal(np.sqrt(n.astype(np.float64)).astype(np.float32), f32)
+    assert np.array_equal(np.sqrt(n.astype(np.float64) + 1e-8).astype(np.float32)[1:], f32[1:])
+    assert np.float32(np.sqrt(np.float64(0) + 1e-8)) == np.float32(1e-4)
