@@ -59,24 +59,58 @@ class Coach:
                     for board, policy, player in zip(board_stacks, policy_planes, players)]
 
     # ---- batched self-play for learn() -----------------------------------------------------------------
-    def selfPlayBatch(self, num_games: int, seed: int = 0, game_id_base: int = 0):
-        """``num_games`` episodes at once on the device -> list of (planes, pi list, v) in the reference's order."""
-        from .selfplay import SelfPlayEngine
-        eng = SelfPlayEngine(num_games, int(self.args.numMCTSSims), self.nnet.predict_batch, cpuct=self.args.cpuct,
+    @staticmethod
+    def _dist():
+        """(rank, world) of the torch.distributed job, (0, 1) outside one."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def selfPlayBatch(self, num_games: int, seed: int = 0, game_id_base: int = 0, gather: bool = False):
+        """``num_games`` episodes at once on the device -> list of (planes, pi list, v) in the reference's order.
+
+        Under torch.distributed the games shard by rank in contiguous blocks (game i plays the same game whichever
+        rank owns it; no collective during self-play) and every rank returns the examples of ITS games -- they stay
+        rank-local and ``NNetWrapper.train`` all-reduces the gradients.  ``gather``: every rank
+        returns the examples of ALL games instead (one all-gather of the un-expanded records, the "final example
+        gather"; the 36-fold expansion happens after it)."""
+        from .selfplay import SelfPlayEngine, build_examples
+        rank, world = self._dist()
+        per = -(-int(num_games) // world)
+        if world > 1 and per * world != num_games:
+            raise ValueError(f"numEps={num_games} must be a multiple of the world size {world}")
+        # on a GPU the net hands its raw binary16 head output to the tree kernel (softmax/tanh fused there)
+        fused = hasattr(self.nnet, "predict_head") and getattr(getattr(self.nnet, "device", None), "type", "cpu") == "cuda"
+        evaluate = self.nnet.predict_head if fused else self.nnet.predict_batch
+        eng = SelfPlayEngine(per, int(self.args.numMCTSSims), evaluate, cpuct=self.args.cpuct,
                              temp_threshold=int(self.args.tempThreshold), seed=seed, max_turns=self.game._max_turns,
-                             game_id_base=game_id_base)
-        eng.play_episode()
+                             game_id_base=game_id_base + rank * per, fused_head=fused)
+        if world > 1:                                   # every rank plays the full episode length (all-gather shapes agree)
+            while eng.move < eng.max_moves:
+                eng.play_move()
+        else:
+            eng.play_episode()
         eng.mcts.raise_on_faults()
-        planes, pi, v = eng.examples()
+        planes, pi, v = build_examples(eng.be, eng.gather_records()) if gather else eng.examples()
         return [(planes[i], pi[i].tolist(), float(v[i])) for i in range(len(v))]
 
     def learn(self):
         pit_interval = 5
         for i in range(1, self.args.numIters + 1):
             log.info(f"Starting Iter #{i} ...")
+            rank, world = self._dist()
             if not self.skipFirstSelfPlay or i > 1:
                 examples = deque([], maxlen=self.args.maxlenOfQueue)
-                examples += self.selfPlayBatch(int(self.args.numEps), seed=int(np.random.randint(0, 2 ** 31 - 1)))
+                seed = int(np.random.randint(0, 2 ** 31 - 1))
+                if world > 1:                            # one seed for the whole job (rank 0's)
+                    import torch
+                    import torch.distributed as dist
+                    t = torch.tensor([seed], dtype=torch.int64, device=getattr(self.nnet, "device", "cpu"))
+                    dist.broadcast(t, 0)
+                    seed = int(t[0])
+                examples += self.selfPlayBatch(int(self.args.numEps), seed=seed,
+                                               gather=bool(dict(self.args).get("gatherExamples", False)))
                 self.trainExamplesHistory.append(examples)
             if len(self.trainExamplesHistory) > self.args.numItersForTrainExamplesHistory:
                 log.warning(f"Removing the oldest entry in trainExamples. len(trainExamplesHistory) = "
@@ -88,7 +122,8 @@ class Coach:
                 train_examples.extend(e)
             shuffle(train_examples)
             self.nnet.train(train_examples)
-            self.nnet.save_checkpoint(folder=self.args.checkpoint, filename="temp.pth.tar")
+            if rank == 0:
+                self.nnet.save_checkpoint(folder=self.args.checkpoint, filename="temp.pth.tar")
             if i % pit_interval != 0:
                 continue
             log.info("PITTING AGAINST BASELINES")
@@ -114,7 +149,9 @@ class Coach:
     def saveTrainExamples(self, iteration):
         folder = self.args.checkpoint
         os.makedirs(folder, exist_ok=True)
-        with open(os.path.join(folder, self.getCheckpointFile(iteration) + ".examples"), "wb+") as f:
+        rank, world = self._dist()                     # rank-local shards under torch.distributed
+        suffix = f".rank{rank}" if world > 1 else ""
+        with open(os.path.join(folder, self.getCheckpointFile(iteration) + ".examples" + suffix), "wb+") as f:
             Pickler(f).dump(self.trainExamplesHistory)
 
     def loadTrainExamples(self):

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "ifx_mcts_status": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_get_roots": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_counters": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ifx_stub_policy_value": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 ERRORS = {-1: "IFX_E_ARG (bad argument)", -2: "IFX_E_CUDA", -3: "IFX_E_NODEVICE"}

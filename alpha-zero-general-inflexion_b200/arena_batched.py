@@ -32,13 +32,33 @@ class BatchedArena:
             return rules.random_actions(states, self.seed ^ 0x5EED, ply, backend=self.be)
         return rules.greedy_actions(states, backend=self.be)
 
-    def playGames(self, num: int):
-        """-> (games won by player 1 / RED / the MCTS player, games won by player 2 / BLUE, draws)."""
+    def playGames(self, num: int, shard: bool = True):
+        """-> (games won by player 1 / RED / the MCTS player, games won by player 2 / BLUE, draws).
+
+        Under torch.distributed (``shard``) the ``num`` games are split into contiguous blocks, one per rank --
+        game i keeps its colour and its RNG stream whichever rank plays it -- and only the three counters are
+        all-reduced; every rank returns the global result."""
         if not (isinstance(num, int) and num >= 2):
             raise ValueError("num must be an int >= 2")
-        red_first = np.arange(num) <= num // 2                                  # Arena.py:126-129
+        import torch.distributed as dist
+        world = dist.get_world_size() if shard and dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        per = -(-num // world)
+        lo, hi = min(num, rank * per), min(num, (rank + 1) * per)
+        total, num = num, hi - lo
+        if num == 0:
+            result = torch.zeros(3, dtype=torch.int64, device=self.be.device)
+        else:
+            result = torch.tensor(self._play(total, lo, hi), dtype=torch.int64, device=self.be.device)
+        if world > 1:
+            dist.all_reduce(result)
+        return tuple(int(x) for x in result.tolist())
+
+    def _play(self, total: int, lo: int, hi: int):
+        num = hi - lo
+        red_first = np.arange(lo, hi) <= total // 2                             # Arena.py:126-129
         starts = pack_states(np.zeros((num, 49), dtype=np.int64), np.where(red_first, 1, -1), 0, 0, self.max_turns,
-                             tags=np.arange(num))
+                             tags=np.arange(lo, hi))
         states = self.be.states_tensor(starts)
         mcts = BatchedMCTS(num, self.num_sims, self.cpuct, seed=self.seed, backend=self.be, fused_head=self.fused_head)
         red_first_t = torch.from_numpy(red_first).to(self.be.device)

@@ -31,27 +31,72 @@ struct alignas(16) IfxGame {       // 64 bytes per game
   int32_t root_slot;               // node slot of the root, -1 while it is not expanded
   int32_t next_slot;               // slot the next expansion will use (popped ahead of time), -1 = pool empty
   int32_t leaf_hpos;               // hash position (first empty probe slot) found when the pending leaf missed
-  int32_t pad;
+  int32_t root_nv;                 // number of valid actions of the root (how much of its rows the wave mirrors)
 };
 
 struct alignas(16) IfxKey { uint64_t k0, k1; };
 struct alignas(16) IfxF4 { float x, y, z, w; };
 struct alignas(16) IfxU4 { uint32_t x, y, z, w; };
 
+// Rows are COMPACT: a node stores P, N and Q only for its valid actions, in ascending action order -- entry i of a
+// row belongs to the i-th valid action.  The valid set of a node is a pure function of its key (own mask x 6
+// spread directions, then the spawn mask: InflexionGame.py:93-100), so nothing but the rows is stored; the
+// reference's scan over all 343 actions with `if valids[a]` (MCTS.py:119-120) visits exactly these entries in
+// exactly this order.  Under random play a node has 86 valid actions on average, so a visit
+// reads 1.5 KB (one 128-entry group of each row) instead of 4.1 KB, and evaluates 4 PUCT terms per lane, not 12.
+//
 // One 32-bit word per edge in the N row:
 //   bits 0..16   visit count N(s,a)              (MCTS.py:27 Nsa)
 //   bits 17..30  child hint: node slot the edge led to last time (0x3FFF = none).  Only a hint -- the key of
 //                that slot is compared with the recomputed child key before it is trusted, because the
 //                reference's table is keyed by planes, not by (s,a)
 //   bit 31       Q of this edge is a Python float (kept in q64)
-//   0xFFFFFFFF   the action is not valid in this node (Vs[s][a] == 0, MCTS.py:109,120)
 #define IFX_N_TAG 0x80000000u
 #define IFX_N_COUNT 0x0001FFFFu
 #define IFX_N_HINT_SHIFT 17
 #define IFX_N_HINT_NONE 0x3FFFu
-#define IFX_N_INVALID 0xFFFFFFFFu
-#define IFX_N_FRESH (IFX_N_HINT_NONE << IFX_N_HINT_SHIFT)      // valid, unvisited, no hint
-IFX_HD uint32_t ifx_n_count(uint32_t raw) { return raw == IFX_N_INVALID ? 0u : (raw & IFX_N_COUNT); }
+#define IFX_N_FRESH (IFX_N_HINT_NONE << IFX_N_HINT_SHIFT)      // unvisited, no hint
+#define IFX_GROUP 128                                          // row entries one warp-wide 128-bit load covers
+
+// the valid actions of a node: own stacks (six spread directions each), then the spawn cells
+struct ValidSet { uint64_t own, spawn; int n_own, nv; };
+IFX_HD ValidSet ifx_valid_set(uint64_t own, uint64_t spawn) {
+  ValidSet V; V.own = own; V.spawn = spawn; V.n_own = ifx_popc64(own); V.nv = 6 * V.n_own + ifx_popc64(spawn);
+  return V;
+}
+IFX_HD ValidSet ifx_valid_set_of_key(const IfxKey& k) {      // from a node key (ifx_key0 / ifx_key1)
+  const uint64_t own = k.k0 & IFX_BOARD_MASK, opp = k.k1 & IFX_BOARD_MASK;
+  return ifx_valid_set(own, ((k.k1 >> 49) & 1ull) ? (~(own | opp) & IFX_BOARD_MASK) : 0ull);
+}
+IFX_HD int ifx_rank64(uint64_t m, int cell) { return ifx_popc64(m & ((1ull << cell) - 1ull)); }
+// number of valid actions with an index below a (= the compact index of a, if a is valid); 0 <= a <= 343
+IFX_HD int ifx_valid_below(const ValidSet& V, int a) {
+  const int m = a / IFX_CELLS, cell = a - m * IFX_CELLS;
+  if (m < IFX_SPAWN) return m * V.n_own + ifx_rank64(V.own, cell);
+  if (m == IFX_SPAWN) return 6 * V.n_own + ifx_rank64(V.spawn, cell);
+  return V.nv;
+}
+#ifdef IFX_HOSTSIM
+static inline int ifx_nth_set_bit64(uint64_t m, int k) {      // position of the k-th (0-based) set bit
+  for (int i = 0; i < 64; ++i) if ((m >> i) & 1ull) { if (k == 0) return i; --k; }
+  return 64;
+}
+#else
+IFX_D int ifx_nth_set_bit64(uint64_t m, int k) {
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  const int c = __popc(lo);
+  return k < c ? (int)__fns(lo, 0u, k + 1) : 32 + (int)__fns(hi, 0u, k - c + 1);
+}
+#endif
+// action index of compact entry ci (0 <= ci < nv)
+IFX_HD int ifx_compact_to_action(const ValidSet& V, int ci) {
+  const int spread = 6 * V.n_own;
+  if (ci < spread) {
+    const int m = ci / V.n_own, k = ci - m * V.n_own;
+    return m * IFX_CELLS + ifx_nth_set_bit64(V.own, k);
+  }
+  return IFX_SPAWN * IFX_CELLS + ifx_nth_set_bit64(V.spawn, ci - spread);
+}
 
 // per-node header: Ns and the two square roots PUCT needs, refreshed whenever Ns changes (off the select path)
 struct alignas(16) IfxHead { int32_t ns; float sq_seen, sq_unseen; int32_t pad; };
@@ -87,6 +132,16 @@ IFX_HD uint32_t ifx_hash_key(uint64_t k0, uint64_t k1) {
   uint64_t h = k0 * 0x9E3779B97F4A7C15ull ^ (k1 + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
   h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
   return (uint32_t)h;
+}
+
+// Every pool is [G][...]: a warp works on ONE game, so the wave kernel rebases the pointers to its game once and
+// passes g = 0 from then on -- the 64-bit `g * stride` products disappear from every address computation.
+IFX_HD TreeParams tree_rebase(const TreeParams& P, int g) {
+  TreeParams L = P;
+  L.rows += (int64_t)g * P.C * 3 * IFX_ROW; L.q64 += (int64_t)g * P.C * 344;
+  L.node_key += (int64_t)g * P.C; L.node_head += (int64_t)g * P.C; L.hash += (int64_t)g * P.H;
+  L.free_stack += (int64_t)g * P.C; L.games += g; L.path += (int64_t)g * IFX_MAX_DEPTH; L.roots += g; L.leaves += g;
+  return L;
 }
 
 IFX_HD float* tree_row(const TreeParams& P, int g, int slot, int which) {
@@ -158,11 +213,16 @@ IFX_D void ifx_cp_async16(void* dst, const void* src) {
 IFX_D void ifx_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
-IFX_D void tree_mirror_fetch(const TreeParams& P, int g, int slot, RootMirror* M) {
+IFX_D void tree_mirror_fetch(const TreeParams& P, int g, int slot, int nv, RootMirror* M) {
+  const int chunks = (nv + 3) >> 2;                         // 16-byte chunks per row that hold entries (<= 88)
   const char* src = reinterpret_cast<const char*>(tree_row(P, g, slot, 0));
   char* dst = reinterpret_cast<char*>(M->rows);
   IFX_FOR_LANES(l) {
-    for (int i = l; i < 3 * IFX_ROW / 4; i += 32) ifx_cp_async16(dst + 16 * i, src + 16 * i);
+    for (int i = l; i < chunks; i += 32) {                  // one pass for nv <= 128
+      ifx_cp_async16(dst + 16 * i, src + 16 * i);
+      ifx_cp_async16(dst + 16 * i + 4 * IFX_ROW, src + 16 * i + 4 * IFX_ROW);
+      ifx_cp_async16(dst + 16 * i + 8 * IFX_ROW, src + 16 * i + 8 * IFX_ROW);
+    }
     if (l == 0) ifx_cp_async16(&M->head, &P.node_head[(int64_t)g * P.C + slot]);
     if (l == 1) ifx_cp_async16(&M->key, &P.node_key[(int64_t)g * P.C + slot]);
   }
@@ -171,7 +231,8 @@ IFX_D void tree_mirror_wait() { ifx_cp_async_wait(); IFX_SYNCWARP(); }
 
 // ---- one edge of the backup (MCTS.py:136-142 under NEP-50 promotion) ----
 // (raw N, Q32) were loaded ahead of time; q64 is touched only for Python-float edges.  `child` (>= 0) refreshes
-// the edge's child hint.  `mirror` (nullable) receives the same N and Q words (the edge belongs to the root).
+// the edge's child hint.  `a` is the edge's compact index in its node's rows.  `mirror` (nullable) receives the
+// same N and Q words (the edge belongs to the root).
 IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, uint32_t raw, float q32, double v, bool v_is32,
                              int child, RootMirror* mirror) {
   uint32_t* nrow = reinterpret_cast<uint32_t*>(tree_row(P, g, slot, 1));
@@ -205,7 +266,7 @@ IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, uint32
   }
 }
 
-// The path lives one level per lane (lane L holds edge L) as {slot << 9 | action, N word, Q bits, Ns}: the
+// The path lives one level per lane (lane L holds edge L) as {slot << 9 | compact index, N word, Q bits, Ns}: the
 // edge statistics were in registers when the edge was selected and nothing else touches this game's tree
 // before its backup, so the backup needs no loads of its own.
 // Back `v` (the value returned by the deepest search() call) up the first `depth` edges of the path; levels
@@ -232,92 +293,69 @@ IFX_D void tree_backup_apply(const TreeParams& P, int g, int depth, const LaneVa
 }
 
 // ---- PUCT arg-max over the valid actions of one node (MCTS.py:114-129) ----
-// The three rows are fetched whole with 128-bit loads (lane l owns actions 4l+128j .. +3) before any use;
-// validity comes with the N row (IFX_N_INVALID), the square roots with the node header.
-// Returns the action (or -1) and the raw N word of the chosen edge (it carries the child hint).
-struct RowRegs { LaneVar<IfxF4> p0, p1, p2, q0, q1, q2; LaneVar<IfxU4> n0, n1, n2; IfxHead head; IfxKey key; };
+// Group j of a node's rows = compact entries 128j .. 128j+127: lane l owns entries 128j+4l .. +3, fetched as one
+// 128-bit load per row.  Group 0 (all a node with <= 128 valid actions has: p95 of random play is 119) is
+// requested as soon as the slot is known, together with the header (square roots) and the key; further groups
+// cost a round trip each and are rare.
+struct RowRegs { LaneVar<IfxF4> p, q; LaneVar<IfxU4> n; IfxHead head; IfxKey key; };
 
-IFX_D void tree_rows_load(const TreeParams& P, int g, int slot, RowRegs& R) {
-  const float* prow = tree_row(P, g, slot, 0);
-  const float* nrow = tree_row(P, g, slot, 1);
-  const float* qrow = tree_row(P, g, slot, 2);
+IFX_D void tree_rows_load_group(const float* rows, int j, RowRegs& R) {
   IFX_FOR_LANES(l) {
-    const int i = 4 * l;
-    R.p0[l] = *reinterpret_cast<const IfxF4*>(prow + i);
-    R.n0[l] = *reinterpret_cast<const IfxU4*>(nrow + i);
-    R.q0[l] = *reinterpret_cast<const IfxF4*>(qrow + i);
-    R.p1[l] = *reinterpret_cast<const IfxF4*>(prow + i + 128);
-    R.n1[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 128);
-    R.q1[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 128);
-    if (i + 256 < IFX_ROW) {
-      R.p2[l] = *reinterpret_cast<const IfxF4*>(prow + i + 256);
-      R.n2[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 256);
-      R.q2[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 256);
-    } else {
-      const IfxF4 zf = {0.f, 0.f, 0.f, 0.f};
-      const IfxU4 zu = {IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID};
-      R.p2[l] = zf; R.q2[l] = zf; R.n2[l] = zu;
+    const int i = IFX_GROUP * j + 4 * l;
+    IfxF4 pv = {0.f, 0.f, 0.f, 0.f}, qv = pv;
+    IfxU4 nv4 = {IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH};
+    if (i < IFX_ROW) {
+      pv = *reinterpret_cast<const IfxF4*>(rows + i);
+      nv4 = *reinterpret_cast<const IfxU4*>(rows + IFX_ROW + i);
+      qv = *reinterpret_cast<const IfxF4*>(rows + 2 * IFX_ROW + i);
     }
+    R.p[l] = pv; R.n[l] = nv4; R.q[l] = qv;
   }
+}
+IFX_D void tree_rows_load(const TreeParams& P, int g, int slot, RowRegs& R) {
+  tree_rows_load_group(tree_row(P, g, slot, 0), 0, R);
   R.head = P.node_head[(int64_t)g * P.C + slot];
   R.key = P.node_key[(int64_t)g * P.C + slot];
 }
-
 IFX_D void tree_rows_from_mirror(const RootMirror* M, RowRegs& R) {
-  const float* prow = M->rows; const float* nrow = M->rows + IFX_ROW; const float* qrow = M->rows + 2 * IFX_ROW;
-  IFX_FOR_LANES(l) {
-    const int i = 4 * l;
-    R.p0[l] = *reinterpret_cast<const IfxF4*>(prow + i);
-    R.n0[l] = *reinterpret_cast<const IfxU4*>(nrow + i);
-    R.q0[l] = *reinterpret_cast<const IfxF4*>(qrow + i);
-    R.p1[l] = *reinterpret_cast<const IfxF4*>(prow + i + 128);
-    R.n1[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 128);
-    R.q1[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 128);
-    if (i + 256 < IFX_ROW) {
-      R.p2[l] = *reinterpret_cast<const IfxF4*>(prow + i + 256);
-      R.n2[l] = *reinterpret_cast<const IfxU4*>(nrow + i + 256);
-      R.q2[l] = *reinterpret_cast<const IfxF4*>(qrow + i + 256);
-    } else {
-      const IfxF4 zf = {0.f, 0.f, 0.f, 0.f};
-      const IfxU4 zu = {IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID, IFX_N_INVALID};
-      R.p2[l] = zf; R.q2[l] = zf; R.n2[l] = zu;
-    }
-  }
+  tree_rows_load_group(M->rows, 0, R);
   R.head = M->head;
   R.key = M->key;
 }
 
-IFX_D int tree_select(const TreeParams& P, const RowRegs& R, uint32_t* chosen_raw, float* chosen_q) {
+// `rows` = where groups beyond the first come from (the node's rows in HBM, or the root mirror).
+// Returns the compact index of the chosen edge (or -1), its raw N word (it carries the child hint) and its Q.
+IFX_D int tree_select(const TreeParams& P, RowRegs& R, const float* rows, int nv, uint32_t* chosen_raw, float* chosen_q) {
   const float sq_seen = R.head.sq_seen, sq_unseen = R.head.sq_unseen;
   LaneVar<float> bu, bq; LaneVar<int> ba; LaneVar<uint32_t> braw;
-  IFX_FOR_LANES(l) {
-    float best = -INFINITY, qsel = 0.0f; int arg = 0x7fffffff; uint32_t raw = 0;
-    // ascending action order inside the lane, strict '>' keeps the lowest index on ties
+  IFX_FOR_LANES(l) { bu[l] = -INFINITY; bq[l] = 0.0f; ba[l] = 0x7fffffff; braw[l] = 0u; }
+  for (int j = 0; IFX_GROUP * j < nv; ++j) {
+    if (j > 0) tree_rows_load_group(rows, j, R);
+    IFX_FOR_LANES(l) {
+      float best = bu[l], qsel = bq[l]; int arg = ba[l]; uint32_t raw = braw[l];
+      // ascending order inside the lane and across groups, strict '>' keeps the lowest index on ties
 #define IFX_PUCT(PV, NV, QV, A)                                                                       \
-    do { /* straight-line (no divergent branches) so the twelve independent chains of a lane interleave */ \
-      const bool ok_ = (NV) != IFX_N_INVALID;                                                         \
-      const uint32_t n_ = (NV) & IFX_N_COUNT;                                                         \
-      const bool seen_ = ok_ && n_ != 0u;                                                             \
-      const float cp = ifx_fmul(P.cpuct, (PV));                                                       \
-      /* a dummy numerator for edges that do not use the quotient keeps 0/x out of the division's slow path */ \
-      const float quo = ifx_fdiv(seen_ ? ifx_fmul(cp, sq_seen) : 1.0f, (float)(1u + n_));             \
-      const float u = seen_ ? ifx_fadd((QV), quo) : ifx_fmul(cp, sq_unseen);                          \
-      if (ok_ && u > best) { best = u; arg = (A); raw = (NV); qsel = (QV); } } while (0)
-#define IFX_PUCT4(PV, NV, QV, BASE)                                                                   \
-    IFX_PUCT(PV.x, NV.x, QV.x, (BASE)); IFX_PUCT(PV.y, NV.y, QV.y, (BASE) + 1);                       \
-    IFX_PUCT(PV.z, NV.z, QV.z, (BASE) + 2); IFX_PUCT(PV.w, NV.w, QV.w, (BASE) + 3)
-    IFX_PUCT4(R.p0[l], R.n0[l], R.q0[l], 4 * l);
-    IFX_PUCT4(R.p1[l], R.n1[l], R.q1[l], 4 * l + 128);
-    IFX_PUCT4(R.p2[l], R.n2[l], R.q2[l], 4 * l + 256);
-#undef IFX_PUCT4
+      do { /* straight-line (no divergent branches) so the four independent chains of a lane interleave */ \
+        const bool ok_ = (A) < nv;                                                                      \
+        const uint32_t n_ = (NV) & IFX_N_COUNT;                                                         \
+        const bool seen_ = ok_ && n_ != 0u;                                                             \
+        const float cp = ifx_fmul(P.cpuct, (PV));                                                       \
+        /* a dummy numerator for edges that do not use the quotient keeps 0/x out of the division's slow path */ \
+        const float quo = ifx_fdiv(seen_ ? ifx_fmul(cp, sq_seen) : 1.0f, (float)(1u + n_));             \
+        const float u = seen_ ? ifx_fadd((QV), quo) : ifx_fmul(cp, sq_unseen);                          \
+        if (ok_ && u > best) { best = u; arg = (A); raw = (NV); qsel = (QV); } } while (0)
+      const int base = IFX_GROUP * j + 4 * l;
+      IFX_PUCT(R.p[l].x, R.n[l].x, R.q[l].x, base);     IFX_PUCT(R.p[l].y, R.n[l].y, R.q[l].y, base + 1);
+      IFX_PUCT(R.p[l].z, R.n[l].z, R.q[l].z, base + 2); IFX_PUCT(R.p[l].w, R.n[l].w, R.q[l].w, base + 3);
 #undef IFX_PUCT
-    bu[l] = best; ba[l] = arg; braw[l] = raw; bq[l] = qsel;
+      bu[l] = best; ba[l] = arg; braw[l] = raw; bq[l] = qsel;
+    }
   }
   float u; int a;
   lanes_argmax(bu, ba, &u, &a);
   if (a == 0x7fffffff) return -1;
-  *chosen_raw = lanes_bcast(braw, (a & 127) >> 2);          // the lane that owns action a
-  *chosen_q = lanes_bcast(bq, (a & 127) >> 2);
+  *chosen_raw = lanes_bcast(braw, (a & (IFX_GROUP - 1)) >> 2);   // the lane that owns entry a (in every group)
+  *chosen_q = lanes_bcast(bq, (a & (IFX_GROUP - 1)) >> 2);
   return a;
 }
 
@@ -413,10 +451,11 @@ IFX_D float tree_head_exp(const uint16_t* head, PolicyRegs& R) {
 }
 
 // ---- expansion of the pending leaf (MCTS.py:89-112) ----
-// returns the slot, or -1 with a fault bit set
+// returns the slot, or -1 with a fault bit set; *leaf_nv = number of valid actions of the new node
 IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, const PolicyRegs& R, float* buf,
-                      const bool fused) {
-  const uint64_t own = ifx_own(leaf), spawn = ifx_spawn_mask(leaf);
+                      const bool fused, int* leaf_nv) {
+  const ValidSet V = ifx_valid_set(ifx_own(leaf), ifx_spawn_mask(leaf));
+  *leaf_nv = V.nv;
   LaneVar<uint32_t> vbits;                                  // validity of the lane's 12 actions (4 bits per group)
   LaneVar<IfxF4> m0, m1, m2;                                // policies *= valids (MCTS.py:95)
   IFX_FOR_LANES(l) {
@@ -425,7 +464,7 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int i = 4 * l + 128 * j;
-      const uint32_t b = tree_valid4(own, spawn, i);
+      const uint32_t b = tree_valid4(V.own, V.spawn, i);
       vb |= b << (4 * j);
       IfxF4 v = R.p[j][l];
       v.x = (b & 1u) ? v.x : 0.0f; v.y = (b & 2u) ? v.y : 0.0f;
@@ -445,10 +484,10 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
     total = lanes_sum_f32(part);
   } else {
     IFX_SYNCWARP();
-    total = tree_pairwise_sum343(buf);                      // policies.sum(), numpy's order
+    total = tree_pairwise_sum343(buf);                      // policies.sum() over the DENSE vector, numpy's order
   }
   const bool uniform = !(total > 0.0f);                     // MCTS.py:98-107: all valid moves masked
-  if (uniform) total = (float)ifx_num_valid(leaf);          // sum of 0/1 values is exact in any order
+  if (uniform) total = (float)V.nv;                         // sum of 0/1 values is exact in any order
   const float inv_total = fused ? ifx_frcp(total) : 0.0f;
   const int slot = G.next_slot;
   if (slot < 0) { G.faults |= IFX_F_POOL; return -1; }
@@ -462,29 +501,28 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int i = 4 * l + 128 * j;
-      if (i < IFX_ROW) {
-        const uint32_t b = (vbits[l] >> (4 * j)) & 0xFu;
+      const uint32_t b = (vbits[l] >> (4 * j)) & 0xFu;
+      if (i < IFX_ACTIONS && b) {                           // (divergent only across lanes with no valid action in the group)
         IfxF4 v = j == 0 ? m0[l] : (j == 1 ? m1[l] : m2[l]);
-        if (uniform) {                                      // policies = valids (MCTS.py:105)
-          v.x = (b & 1u) ? 1.0f : 0.0f; v.y = (b & 2u) ? 1.0f : 0.0f;
-          v.z = (b & 4u) ? 1.0f : 0.0f; v.w = (b & 8u) ? 1.0f : 0.0f;
-        }
-        // policies /= sum.  Invalid entries are exactly 0 either way; dividing a dummy 1.0 for them keeps the
-        // zero numerators out of the IEEE division's slow path (which the whole warp would otherwise take).
-        if (fused) {                                        // one reciprocal, twelve multiplies (masked entries stay 0)
+        if (uniform) { v.x = v.y = v.z = v.w = 1.0f; }       // policies = valids (MCTS.py:105)
+        if (fused) {                                        // one reciprocal, then multiplies
           v.x *= inv_total; v.y *= inv_total; v.z *= inv_total; v.w *= inv_total;
         } else {
-          const float qx = ifx_fdiv((b & 1u) ? v.x : 1.0f, total), qy = ifx_fdiv((b & 2u) ? v.y : 1.0f, total);
-          const float qz = ifx_fdiv((b & 4u) ? v.z : 1.0f, total), qw = ifx_fdiv((b & 8u) ? v.w : 1.0f, total);
-          v.x = (b & 1u) ? qx : 0.0f; v.y = (b & 2u) ? qy : 0.0f; v.z = (b & 4u) ? qz : 0.0f; v.w = (b & 8u) ? qw : 0.0f;
+          // policies /= sum.  A dummy 1.0 for the invalid entries of the group keeps zero numerators out of the
+          // IEEE division's slow path (which the whole warp would otherwise take).
+          v.x = ifx_fdiv((b & 1u) ? v.x : 1.0f, total); v.y = ifx_fdiv((b & 2u) ? v.y : 1.0f, total);
+          v.z = ifx_fdiv((b & 4u) ? v.z : 1.0f, total); v.w = ifx_fdiv((b & 8u) ? v.w : 1.0f, total);
         }
-        *reinterpret_cast<IfxF4*>(prow + i) = v;
-        IfxU4 z;                                             // Vs[s] folded into the N row (MCTS.py:109)
-        z.x = (b & 1u) ? IFX_N_FRESH : IFX_N_INVALID; z.y = (b & 2u) ? IFX_N_FRESH : IFX_N_INVALID;
-        z.z = (b & 4u) ? IFX_N_FRESH : IFX_N_INVALID; z.w = (b & 8u) ? IFX_N_FRESH : IFX_N_INVALID;
-        *reinterpret_cast<IfxU4*>(nrow + i) = z;
+        // compact position of a valid action = number of valid actions below it
+        int c = ifx_valid_below(V, i);
+        if (b & 1u) { prow[c] = v.x; c += 1; }
+        if (b & 2u) { prow[c] = v.y; c += 1; }
+        if (b & 4u) { prow[c] = v.z; c += 1; }
+        if (b & 8u) { prow[c] = v.w; }
       }
     }
+    const IfxU4 z = {IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH};   // Nsa = 0 for every valid action
+    for (int c4 = 4 * l; c4 < V.nv; c4 += 128) *reinterpret_cast<IfxU4*>(nrow + c4) = z;
   }
   const uint64_t k0 = ifx_key0(leaf), k1 = ifx_key1(leaf);
   if (IFX_LANE0) {
@@ -508,17 +546,37 @@ IFX_D int tree_draw_symmetry(const TreeParams& P, const IfxGame& G) {
   return (int)(r.w[0] % 6u) + 6 * (int)(r.w[1] % 7u) + 42 * (int)(r.w[2] % 3u);
 }
 
-// planes of `st` under symmetry `sym` -> float32 [4][49] (the net's input row of this game)
-IFX_D void tree_write_nn_input(const ifx_state& st, int sym, float* out) {
+// Source cell of every (symmetry, destination cell): 126 x 64 bytes, filled once per process by
+// tree_sym_lut_kernel (ifx_mcts_create).  Two coalesced byte loads per lane replace ~130 instructions of index
+// arithmetic per leaf; the loads are issued as soon as the symmetry is drawn, i.e. under the hash probe.
+#ifdef IFX_HOSTSIM
+struct SymSrc { LaneVar<int> a, b; };
+static inline void tree_sym_src_issue(int sym, SymSrc& S) {
+  for (int l = 0; l < 32; ++l) { S.a[l] = ifx_sym_src(sym, l); S.b[l] = l + 32 < IFX_CELLS ? ifx_sym_src(sym, l + 32) : 0; }
+}
+#else
+__device__ uint8_t g_ifx_sym_lut[126 * 64];
+struct SymSrc { LaneVar<int> a, b; };
+IFX_D void tree_sym_src_issue(int sym, SymSrc& S) {
+  const uint8_t* row = g_ifx_sym_lut + sym * 64 + (threadIdx.x & 31u);
+  S.a.v = row[0]; S.b.v = row[32];
+}
+#endif
+
+// planes of `st` under the symmetry whose source cells are S -> float32 [4][49] (the net's input row of this game)
+IFX_D void tree_write_nn_input(const ifx_state& st, const SymSrc& S, float* out) {
   const uint64_t own = ifx_own(st), opp = ifx_opp(st);
   const float turn = (float)st.turn, spawn = ifx_can_spawn(st) ? 1.0f : 0.0f;
   IFX_FOR_LANES(l) {
-    for (int cell = l; cell < IFX_CELLS; cell += 32) {
-      const int src = ifx_sym_src(sym, cell);
-      out[cell] = (float)((own >> src) & 1ull);
-      out[IFX_CELLS + cell] = (float)((opp >> src) & 1ull);
-      out[2 * IFX_CELLS + cell] = turn;
-      out[3 * IFX_CELLS + cell] = spawn;
+    out[l] = (float)((own >> S.a[l]) & 1ull);
+    out[IFX_CELLS + l] = (float)((opp >> S.a[l]) & 1ull);
+    out[2 * IFX_CELLS + l] = turn;
+    out[3 * IFX_CELLS + l] = spawn;
+    if (l + 32 < IFX_CELLS) {
+      out[l + 32] = (float)((own >> S.b[l]) & 1ull);
+      out[IFX_CELLS + l + 32] = (float)((opp >> S.b[l]) & 1ull);
+      out[2 * IFX_CELLS + l + 32] = turn;
+      out[3 * IFX_CELLS + l + 32] = spawn;
     }
   }
 }
@@ -531,8 +589,11 @@ IFX_D uint64_t ifx_now_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltime
 #endif
 
 template <bool DBG>
-IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_t pi_stride, const float* nn_v,
+IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int64_t pi_stride, const float* nn_v,
                           float* nn_in, float* buf, RootMirror* mirror) {
+  const TreeParams P = tree_rebase(P0, g0);
+  const int g = 0;
+  nn_in += (int64_t)g0 * 196;
   const uint64_t dbg_t0 = DBG ? ifx_now_ns() : 0;
   uint64_t dbg_t1 = 0, dbg_t2 = 0, dbg_t3 = 0, dbg_t4 = 0;
   int dbg_depth = 0, dbg_probes = 0;
@@ -542,15 +603,15 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   // the root's rows start moving into shared memory the moment the record is here; they land while the pending
   // leaf is expanded and backed up
   int mirror_slot = G.root_slot;
-  if (mirror_slot >= 0) tree_mirror_fetch(P, g, mirror_slot, mirror);
+  if (mirror_slot >= 0) tree_mirror_fetch(P, g, mirror_slot, G.root_nv, mirror);
   const ifx_state leaf = P.leaves[g];
   float leaf_v;
   PolicyRegs pol;
   if (P.logits == 2) {                                      // binary16 head output: exp + tanh fused here
-    leaf_v = tree_head_exp(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g * pi_stride, pol);
+    leaf_v = tree_head_exp(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g0 * pi_stride, pol);
   } else {
-    leaf_v = nn_v[g];
-    const float* pi_row = nn_pi + (int64_t)g * pi_stride;
+    leaf_v = nn_v[g0];
+    const float* pi_row = nn_pi + (int64_t)g0 * pi_stride;
     tree_policy_load(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, pol);
   }
   LaneVar<IfxU4> path;
@@ -558,11 +619,12 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   if (G.faults) { if (mirror_slot >= 0) tree_mirror_wait(); return; }
   if (DBG) dbg_t1 = ifx_now_ns() + (uint64_t)(G.pending & 0) + (uint64_t)(leaf.turn & 0);
   if (G.pending) {
-    const int slot = tree_expand(P, g, G, leaf, pol, buf, P.logits == 2);
+    int leaf_nv = 0;
+    const int slot = tree_expand(P, g, G, leaf, pol, buf, P.logits == 2, &leaf_nv);
     if (DBG) dbg_t2 = ifx_now_ns();
     if (mirror_slot >= 0) tree_mirror_wait();               // the backup patches the mirror: it must have landed
     if (slot >= 0) {
-      if (G.path_len == 0) G.root_slot = slot;              // the root itself was the leaf
+      if (G.path_len == 0) { G.root_slot = slot; G.root_nv = leaf_nv; }   // the root itself was the leaf
       // search() of the leaf returns -v, v a float32 (MCTS.py:112; NNet.py:94)
       tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot, mirror_slot >= 0 ? mirror : nullptr);
       G.sims_done += 1; G.n_sims += 1;
@@ -582,7 +644,7 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
     bool inflight = slot >= 0;
     if (inflight) {
       if (mirror_slot != slot) {                            // the root was expanded in this very wave (once per move at most)
-        tree_mirror_fetch(P, g, slot, mirror);
+        tree_mirror_fetch(P, g, slot, G.root_nv, mirror);
         tree_mirror_wait();
         mirror_slot = slot;
       }
@@ -607,6 +669,8 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
         LaneVar<IfxKey> first;
         tree_hash_issue(P, g, h, first);
         const int sym = tree_draw_symmetry(P, G);
+        SymSrc sym_src;
+        tree_sym_src_issue(sym, sym_src);
         slot = tree_hash_resolve(P, g, k0, k1, h, first, &miss_pos);
         if (DBG) dbg_probes += 1;
         if (slot >= 0) {
@@ -614,22 +678,25 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
         } else {                                            // MCTS.py:89: leaf -> wait for the net
           if (IFX_LANE0) P.leaves[g] = st;
           IFX_FOR_LANES(l) { if (l < depth) P.path[(int64_t)g * IFX_MAX_DEPTH + l] = path[l]; }
-          tree_write_nn_input(st, sym, nn_in + (int64_t)g * 196);
+          tree_write_nn_input(st, sym_src, nn_in);
           G.path_len = depth; G.pending = 1; G.leaf_hpos = miss_pos;
           break;
         }
       }
       G.n_visits += 1;
       uint32_t raw = 0; float qsel = 0.0f;
-      const int a = tree_select(P, rows, &raw, &qsel);
-      if (a < 0) { G.faults |= IFX_F_NOVALID; break; }
+      const ValidSet V = ifx_valid_set(ifx_own(st), ifx_spawn_mask(st));
+      const bool at_root = depth == 0 && slot == mirror_slot;
+      const int ci = tree_select(P, rows, at_root ? mirror->rows : tree_row(P, g, slot, 0), V.nv, &raw, &qsel);
+      if (ci < 0) { G.faults |= IFX_F_NOVALID; break; }
       if (depth >= P.maxd) { G.faults |= IFX_F_DEPTH; break; }
       IFX_FOR_LANES(l) {
         if (l == depth) {
-          IfxU4 e; e.x = ((uint32_t)slot << 9) | (uint32_t)a; e.y = raw; e.z = ifx_f2u(qsel); e.w = (uint32_t)rows.head.ns;
+          IfxU4 e; e.x = ((uint32_t)slot << 9) | (uint32_t)ci; e.y = raw; e.z = ifx_f2u(qsel); e.w = (uint32_t)rows.head.ns;
           path[l] = e;
         }
       }
+      const int a = ifx_compact_to_action(V, ci);
       depth += 1;
       if (DBG && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
       if (DBG) dbg_depth = depth > dbg_depth ? depth : dbg_depth;
@@ -645,7 +712,7 @@ IFX_D void tree_wave_game(const TreeParams& P, int g, const float* nn_pi, int64_
   }
   if (IFX_LANE0) P.games[g] = G;
   if (DBG && IFX_LANE0) {
-    uint64_t* d = P.debug + (int64_t)g * 8;
+    uint64_t* d = P.debug + (int64_t)g0 * 8;
     d[0] = dbg_t0; d[1] = dbg_t1; d[2] = dbg_t2; d[3] = dbg_t3; d[4] = dbg_t4; d[5] = ifx_now_ns();
     d[6] = (uint64_t)dbg_depth; d[7] = (uint64_t)dbg_probes;
   }
@@ -728,6 +795,7 @@ IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
   G.free_top = free_top;
   G.n_live = live;
   G.root_slot = root_slot;
+  G.root_nv = ifx_valid_set(ifx_own(root), ifx_spawn_mask(root)).nv;
   G.pending = 0;
   G.path_len = 0;
   G.leaf_hpos = -1;
@@ -746,11 +814,12 @@ IFX_D int tree_sample_action(const TreeParams& P, int g, int temp_threshold, int
   const int slot = G.root_slot;
   if (slot < 0) return -1;
   const uint32_t* nrow = reinterpret_cast<const uint32_t*>(tree_row(P, g, slot, 1));
+  const ValidSet V = ifx_valid_set(ifx_own(root), ifx_spawn_mask(root));
   LaneVar<int> lmax, lsum;
   IFX_FOR_LANES(l) {
     int mx = 0, sm = 0;
     for (int a = l; a < IFX_ROW; a += 32) {
-      const int c = a < IFX_ACTIONS ? (int)ifx_n_count(nrow[a]) : 0;
+      const int c = (a < IFX_ACTIONS && tree_action_bit(V.own, V.spawn, a)) ? (int)(nrow[ifx_valid_below(V, a)] & IFX_N_COUNT) : 0;
       buf[a] = c; mx = c > mx ? c : mx; sm += c;
     }
     lmax[l] = mx; lsum[l] = sm;

@@ -93,15 +93,19 @@ IFX_D void body_root_stats(const TreeParams& P, int g, int32_t* counts, float* q
   const uint32_t* nrow = slot >= 0 ? reinterpret_cast<const uint32_t*>(tree_row(P, g, slot, 1)) : nullptr;
   const float* qrow = slot >= 0 ? tree_row(P, g, slot, 2) : nullptr;
   const double* qd = slot >= 0 ? P.q64 + ((int64_t)g * P.C + slot) * 344 : nullptr;
+  const ifx_state root = P.roots[g];
+  const ValidSet V = ifx_valid_set(ifx_own(root), ifx_spawn_mask(root));   // rows are compact: entry = rank among valid actions
   IFX_FOR_LANES(l) {
     for (int a = l; a < IFX_ACTIONS; a += 32) {
-      const uint32_t raw = nrow ? nrow[a] : 0u;
-      const uint32_t n = ifx_n_count(raw);
-      const bool is64 = raw != IFX_N_INVALID && (raw & IFX_N_TAG) != 0;
+      const bool valid = nrow && tree_action_bit(V.own, V.spawn, a);
+      const int ci = valid ? ifx_valid_below(V, a) : 0;
+      const uint32_t raw = valid ? nrow[ci] : 0u;
+      const uint32_t n = raw & IFX_N_COUNT;
+      const bool is64 = (raw & IFX_N_TAG) != 0;
       const int64_t o = (int64_t)g * IFX_ACTIONS + a;
       if (counts) counts[o] = (int32_t)n;
-      if (q32) q32[o] = n ? qrow[a] : 0.0f;
-      if (q64) q64[o] = n ? (is64 ? qd[a] : (double)qrow[a]) : 0.0;
+      if (q32) q32[o] = n ? qrow[ci] : 0.0f;
+      if (q64) q64[o] = n ? (is64 ? qd[ci] : (double)qrow[ci]) : 0.0;
       if (qkind) qkind[o] = (uint8_t)(n && !is64);
     }
   }
@@ -118,14 +122,20 @@ IFX_D void body_status(const TreeParams& P, int g, int32_t* status) {
 
 #ifndef IFX_HOSTSIM
 // One warp per CTA: a game's slot is handed to the next game the moment its simulation ends (with four warps per
-// CTA the three siblings of a deep game idle until it finishes).  20 resident CTAs per SM = 86 registers, no spills.
+// CTA the three siblings of a deep game idle until it finishes).  Compiled for 32 resident CTAs per SM (the hardware
+// limit; 56 registers, no spills; ~6 KB of shared memory each): 4 736 warp slots, so the 4 096 games of the bench
+// workload run as ONE generation.
 #ifndef TREE_WARPS
 #define TREE_WARPS 1
 #endif
 #define TREE_BLOCK (TREE_WARPS * 32)
 #ifndef IFX_WAVE_MIN_BLOCKS
-#define IFX_WAVE_MIN_BLOCKS 20     // resident CTAs per SM the wave kernel is compiled for (register cap 65536/(32*n))
+#define IFX_WAVE_MIN_BLOCKS 32     // resident CTAs per SM the wave kernel is compiled for (register cap 65536/(32*n))
 #endif
+
+__global__ void tree_sym_lut_kernel() {                      // <<<126, 64>>>: one block per symmetry
+  g_ifx_sym_lut[blockIdx.x * 64 + threadIdx.x] = threadIdx.x < IFX_CELLS ? (uint8_t)ifx_sym_src(blockIdx.x, threadIdx.x) : 0;
+}
 
 template <bool DBG>
 __global__ void __launch_bounds__(TREE_BLOCK, IFX_WAVE_MIN_BLOCKS)
@@ -244,6 +254,8 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   // register-limited number of CTAs per SM (IFX_WAVE_MIN_BLOCKS) is also what shared memory allows
   cudaFuncSetAttribute(tree_wave_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(tree_wave_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  tree_sym_lut_kernel<<<126, 64>>>();                       // idempotent; ordered before any later launch of this process
+  if (cudaDeviceSynchronize() != cudaSuccess) { delete m; return ifx_set_cuda_error((int)cudaGetLastError()); }
 #endif
   *out = m;
   return IFX_OK;

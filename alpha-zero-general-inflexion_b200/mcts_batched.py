@@ -216,8 +216,27 @@ class BatchedMCTS:
             count = int(np.prod(shape))
             return np.frombuffer(ws, dtype=dtype, count=count, offset=off).reshape(shape)
         rows = view(L.rows, np.uint32, (g, n, 3, 352))
-        return {
-            "P": rows[:, :, 0, :343].view(np.float32), "Nraw": rows[:, :, 1, :343], "Q32": rows[:, :, 2, :343].view(np.float32),
-            "Q64": view(L.q64, np.float64, (g, n, 344))[:, :, :343],
-            "key": view(L.node_key, np.uint64, (g, n, 2)), "ns": view(L.node_head, np.int32, (g, n, 4))[:, :, 0],
-        }
+        q64c = view(L.q64, np.float64, (g, n, 344))
+        keys = view(L.node_key, np.uint64, (g, n, 2))
+        # rows are compact (entry i = the i-th valid action of the node, the valid set being a function of the node
+        # key); expand them to dense [343] rows: invalid actions read P = 0, Nraw = 0xFFFFFFFF, Q = 0
+        P = np.zeros((g, n, 343), np.float32)
+        N = np.full((g, n, 343), 0xFFFFFFFF, np.uint32)
+        Q32 = np.zeros((g, n, 343), np.float32)
+        Q64 = np.zeros((g, n, 343), np.float64)
+        board = (1 << 49) - 1
+        for gi in range(g):
+            for slot in np.nonzero(keys[gi, :, 0] != np.uint64(2 ** 64 - 1))[0]:
+                k0, k1 = int(keys[gi, slot, 0]), int(keys[gi, slot, 1])
+                own, opp = k0 & board, k1 & board
+                spawn = (~(own | opp) & board) if (k1 >> 49) & 1 else 0
+                valid = [m * 49 + c for m in range(6) for c in range(49) if (own >> c) & 1]
+                valid += [6 * 49 + c for c in range(49) if (spawn >> c) & 1]
+                idx = np.asarray(valid, dtype=np.int64)
+                k = len(idx)
+                P[gi, slot, idx] = rows[gi, slot, 0, :k].view(np.float32)
+                N[gi, slot, idx] = rows[gi, slot, 1, :k]
+                Q32[gi, slot, idx] = rows[gi, slot, 2, :k].view(np.float32)
+                Q64[gi, slot, idx] = q64c[gi, slot, :k]
+        return {"P": P, "Nraw": N, "Q32": Q32, "Q64": Q64, "key": keys,
+                "ns": view(L.node_head, np.int32, (g, n, 4))[:, :, 0]}

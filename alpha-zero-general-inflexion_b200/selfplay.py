@@ -54,6 +54,7 @@ class SelfPlayEngine:
         self._graph = None
         self.move = 0
         self.my_launches = 0                                      # kernels of libifx_b200 launched (bench evidence)
+        self.extra_launches_per_search = 0                        # library kernels inside `evaluate` (the stub evaluator)
         self.restart()
 
     # ---- episode control ----------------------------------------------------------------------------
@@ -107,7 +108,7 @@ class SelfPlayEngine:
                 wave_timer(self.mcts.wave)
                 self._net_only()
             wave_timer(self.mcts.wave)
-        self.my_launches += self.num_sims + 1
+        self.my_launches += self.num_sims + 1 + self.extra_launches_per_search
 
     def _net_only(self) -> None:
         """Net forward as plain stream launches (timed mode): the stream stays continuously fed, so the event pair
@@ -180,61 +181,94 @@ class SelfPlayEngine:
         self.move += 1
 
     # ---- training examples (Coach.py:74-90) ----------------------------------------------------------
+    def records(self) -> dict:
+        """The un-expanded self-play record of this rank: per move and game slot the root state, the state after the
+        move, the root visit counts and the action (1.5 KB per move; the 36-fold expansion happens in ``examples``)."""
+        assert self.record
+        n = min(self.move, self.max_moves)
+        return {"states": self.ex_states[:n], "after": self.ex_after[:n], "counts": self.ex_counts[:n],
+                "actions": self.ex_actions[:n], "temp_threshold": self.temp_threshold}
+
+    def gather_records(self) -> dict:
+        """The final example gather (BASELINE.json north_star): all ranks' un-expanded records
+        concatenated along the game axis with one all-gather per field (NCCL on GPUs) -- never the expanded set,
+        which is 36x larger.  Every rank must have played the same number of moves and games."""
+        import torch.distributed as dist
+        rec = self.records()
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return rec
+        world = dist.get_world_size()
+        out = {"temp_threshold": rec["temp_threshold"]}
+        for k in ("states", "after", "counts", "actions"):
+            t = rec[k].contiguous()
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            out[k] = torch.cat(parts, dim=1)
+        return out
+
     def examples(self, games=None, fix_alignment: bool = False, expand_symmetries: bool = True):
         """-> (planes int64 [E,4,7,7], pi float64 [E,343], v float64 [E]) for every FINISHED episode of the selected
-        game slots, in the reference's order: per episode, per move, the 36 symmetric forms (Coach.py:77-78,89-90).
+        game slots of this rank; see ``build_examples``."""
+        return build_examples(self.be, self.records(), games, fix_alignment, expand_symmetries)
 
-        Value targets follow Coach.py:89-90.  The reference extends ``players`` by the cumulative example count
-        (Coach.py:79), so entry i of the zip pairs example i with players[i] where players = [P1]*36 + [P2]*72 +
-        [P1]*108 + ...; that quirk is reproduced unless ``fix_alignment``."""
-        assert self.record
-        n_moves = min(self.move, self.max_moves)
-        dev = self.be.device
-        st_all = self.ex_states[:n_moves].cpu().numpy().view(STATE_DTYPE).reshape(n_moves, self.G)
-        after_all = self.ex_after[:n_moves].cpu().numpy().view(STATE_DTYPE).reshape(n_moves, self.G)
-        acts_all = self.ex_actions[:n_moves].cpu().numpy()
-        games = list(range(self.G) if games is None else games)
-        per = 36 if expand_symmetries else 1
-        value_of = {0: 0.0, 1: 1e-4, 2: 1.0, 3: -1.0}
-        # 1. finished episodes: (slot, first move, last move); value targets per example (host, tiny)
-        sel_mv, sel_g, values = [], [], []
-        for g in games:
-            start = 0
-            for mv in range(n_moves):
-                if acts_all[mv, g] < 0:                       # slot idle (game over, no restart)
-                    start = mv + 1
-                    continue
-                if after_all[mv, g]["outcome"] == 0:
-                    continue
-                rows = np.arange(start, mv + 1)               # one finished episode: moves start..mv of slot g
+
+def build_examples(be, rec: dict, games=None, fix_alignment: bool = False, expand_symmetries: bool = True):
+    """Training examples from a self-play record (``SelfPlayEngine.records`` / ``gather_records``) ->
+    (planes int64 [E,4,7,7], pi float64 [E,343], v float64 [E]) for every FINISHED episode of the selected game
+    slots, in the reference's order: per episode, per move, the 36 symmetric forms (Coach.py:77-78,89-90).
+
+    Value targets follow Coach.py:89-90.  The reference extends ``players`` by the cumulative example count
+    (Coach.py:79), so entry i of the zip pairs example i with players[i] where players = [P1]*36 + [P2]*72 +
+    [P1]*108 + ...; that quirk is reproduced unless ``fix_alignment``."""
+    ex_states, ex_after, ex_counts, ex_actions = rec["states"], rec["after"], rec["counts"], rec["actions"]
+    temp_threshold = int(rec["temp_threshold"])
+    n_moves, G = ex_actions.shape[0], ex_actions.shape[1]
+    dev = be.device
+    st_all = ex_states.cpu().numpy().view(STATE_DTYPE).reshape(n_moves, G)
+    after_all = ex_after.cpu().numpy().view(STATE_DTYPE).reshape(n_moves, G)
+    acts_all = ex_actions.cpu().numpy()
+    games = list(range(G) if games is None else games)
+    per = 36 if expand_symmetries else 1
+    value_of = {0: 0.0, 1: 1e-4, 2: 1.0, 3: -1.0}
+    # 1. finished episodes: (slot, first move, last move); value targets per example (host, tiny)
+    sel_mv, sel_g, values = [], [], []
+    for g in games:
+        start = 0
+        for mv in range(n_moves):
+            if acts_all[mv, g] < 0:                       # slot idle (game over, no restart)
                 start = mv + 1
-                played = len(rows)
-                movers = np.where(st_all[rows, g]["player"] == 0, 1, -1)   # side to move of each recorded state
-                final = after_all[mv, g]
-                end_player = 1 if final["player"] == 0 else -1
-                result = value_of[int(final["outcome"])]
-                if fix_alignment or per == 1:
-                    players = np.repeat(movers, per)
-                else:
-                    players = np.concatenate([np.full(per * (i + 1), movers[i]) for i in range(played)])[: per * played]
-                values.append(np.where(players == end_player, result, -result).astype(np.float64))
-                sel_mv.append(rows)
-                sel_g.append(np.full(played, g))
-        if not sel_mv:
-            return np.zeros((0, 4, 7, 7), np.int64), np.zeros((0, 343)), np.zeros(0)
-        mv_idx = torch.from_numpy(np.concatenate(sel_mv)).to(dev)
-        g_idx = torch.from_numpy(np.concatenate(sel_g)).to(dev)
-        # 2. planes, pi and their 36 symmetric forms for ALL selected (move, game) pairs in a handful of kernel calls
-        states = self.ex_states[mv_idx, g_idx].contiguous()
-        planes = rules.planes(states, dtype=torch.int64, backend=self.be)
-        counts = self.ex_counts[mv_idx, g_idx].to(torch.float64)
-        acts = self.ex_actions[mv_idx, g_idx].long()
-        ep_move = torch.from_numpy(np.concatenate([np.arange(len(r)) for r in sel_mv])).to(dev)
-        pi = counts / counts.sum(dim=1, keepdim=True)                                    # MCTS.py:58-60 at temp 1
-        onehot = torch.zeros_like(pi)
-        onehot[torch.arange(len(acts), device=dev), acts] = 1.0                          # MCTS.py:51-56 at temp 0
-        pi = torch.where(((ep_move + 1) < self.temp_threshold)[:, None], pi, onehot)
-        if expand_symmetries:
-            planes = rules.symmetries(planes.contiguous(), backend=self.be).reshape(-1, 4, 7, 7)
-            pi = rules.symmetries(pi.reshape(-1, 7, 7, 7).contiguous(), backend=self.be).reshape(-1, 343)
-        return planes.cpu().numpy(), pi.cpu().numpy(), np.concatenate(values)
+                continue
+            if after_all[mv, g]["outcome"] == 0:
+                continue
+            rows = np.arange(start, mv + 1)               # one finished episode: moves start..mv of slot g
+            start = mv + 1
+            played = len(rows)
+            movers = np.where(st_all[rows, g]["player"] == 0, 1, -1)   # side to move of each recorded state
+            final = after_all[mv, g]
+            end_player = 1 if final["player"] == 0 else -1
+            result = value_of[int(final["outcome"])]
+            if fix_alignment or per == 1:
+                players = np.repeat(movers, per)
+            else:
+                players = np.concatenate([np.full(per * (i + 1), movers[i]) for i in range(played)])[: per * played]
+            values.append(np.where(players == end_player, result, -result).astype(np.float64))
+            sel_mv.append(rows)
+            sel_g.append(np.full(played, g))
+    if not sel_mv:
+        return np.zeros((0, 4, 7, 7), np.int64), np.zeros((0, 343)), np.zeros(0)
+    mv_idx = torch.from_numpy(np.concatenate(sel_mv)).to(dev)
+    g_idx = torch.from_numpy(np.concatenate(sel_g)).to(dev)
+    # 2. planes, pi and their 36 symmetric forms for ALL selected (move, game) pairs in a handful of kernel calls
+    states = ex_states[mv_idx, g_idx].contiguous()
+    planes = rules.planes(states, dtype=torch.int64, backend=be)
+    counts = ex_counts[mv_idx, g_idx].to(torch.float64)
+    acts = ex_actions[mv_idx, g_idx].long()
+    ep_move = torch.from_numpy(np.concatenate([np.arange(len(r)) for r in sel_mv])).to(dev)
+    pi = counts / counts.sum(dim=1, keepdim=True)                                    # MCTS.py:58-60 at temp 1
+    onehot = torch.zeros_like(pi)
+    onehot[torch.arange(len(acts), device=dev), acts] = 1.0                          # MCTS.py:51-56 at temp 0
+    pi = torch.where(((ep_move + 1) < temp_threshold)[:, None], pi, onehot)
+    if expand_symmetries:
+        planes = rules.symmetries(planes.contiguous(), backend=be).reshape(-1, 4, 7, 7)
+        pi = rules.symmetries(pi.reshape(-1, 7, 7, 7).contiguous(), backend=be).reshape(-1, 343)
+    return planes.cpu().numpy(), pi.cpu().numpy(), np.concatenate(values)

@@ -45,6 +45,22 @@ def _mix(h):
     return (h ^ (h >> 15)) & _MASK31
 
 
+def stub_kernel_evaluator(mcts, mode: str = "float"):
+    """The same stub as ONE kernel of libifx_b200 (csrc/ifx_stub.cu), writing straight into the search's net-output
+    buffers: evaluate(nn_in) -> (mcts.nn_pi, mcts.nn_v), so BatchedMCTS.feed copies nothing.  For tree-and-rules-only
+    throughput runs, where the torch version below (a dozen elementwise launches) would dominate the step."""
+    be = mcts.be
+    coef = _coef(be.device)
+    assert not mcts.fused_head
+
+    def evaluate(nn_in):
+        be.check(be.dll.ifx_stub_policy_value(nn_in.data_ptr(), nn_in.shape[0], coef.data_ptr(), int(mode == "dyadic"),
+                                              mcts.nn_pi.data_ptr(), mcts.nn_pi.stride(0), mcts.nn_v.data_ptr(),
+                                              be.stream()))
+        return mcts.nn_pi, mcts.nn_v
+    return evaluate
+
+
 def stub_policy_value(planes: torch.Tensor, mode: str = "float"):
     """mode "dyadic": integer priors in [1,256] (every partial sum exact in float32, any order);
     mode "float": priors k/1000003 (inexact, so the float32 summation ORDER is observable)."""

@@ -185,6 +185,15 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    of this same command (profiles/traffic.json, written by tools/summarize_profiles.py); None if not captured."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel][workload]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def workload_config(a, per_gpu_games, note=None):
     cfg = {"workload": f"batched Inflexion self-play, {per_gpu_games} concurrent games x {a.sims} sims/move per GPU, "
                        f"{a.net} net, 7x7 board, max_turns=343, cpuct=1, tempThreshold=30",
@@ -206,7 +215,7 @@ def run_ours(a):
     import inflexion_b200  # noqa: F401
     from inflexion_b200.backend import Backend
     from inflexion_b200.selfplay import SelfPlayEngine
-    from inflexion_b200.stubnet import stub_policy_value
+    from inflexion_b200.stubnet import stub_kernel_evaluator
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -232,11 +241,14 @@ def run_ours(a):
         nnet = NNetWrapper(InflexionGame(7, max_turns=343, max_power=6), device=be.device)
         evaluate, fused = nnet.predict_head, True          # last GEMM -> tree kernel (softmax/tanh fused there)
     else:
-        evaluate, fused = (lambda x: stub_policy_value(x)), False  # noqa: E731
+        evaluate, fused = None, False                      # installed below: the stub is a kernel of the library
 
     eng = SelfPlayEngine(a.games, a.sims, evaluate, cpuct=1.0, temp_threshold=30, seed=2023, max_turns=343,
                          game_id_base=rank * a.games, record=True, backend=be, fused_head=fused,
                          auto_restart=True, restart_stride=world * a.games)
+    if a.net == "stub":                                    # deterministic stub evaluator, one kernel per wave (csrc/ifx_stub.cu)
+        eng.evaluate = stub_kernel_evaluator(eng.mcts)
+        eng.extra_launches_per_search = a.sims
 
     def barrier():
         torch.cuda.synchronize()
@@ -354,7 +366,7 @@ def run_ours(a):
             "data": "synthetic", "games_per_s": value / (a.sims * MOVES_PER_GAME),
             "config": workload_config(a, a.games),
             "roofline": {"kernel": "tree_wave_kernel", "bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": tree_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": tree_gbs / hbm_peak, "traffic": ncu_traffic("tree_wave_kernel", a.net), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": tree_bytes / max(n_tree, 1), "avg_launch_us": 1e3 * tree_ms / max(n_tree, 1),
                          "launches": n_tree, "share_of_step": tree_ms / instr_ms,
                          "measured_in": "instrumented pass of the same K steps (waves outside the CUDA graph, event pairs recorded "
@@ -425,7 +437,8 @@ def run_rules(a):
         "config": {"workload": f"rules kernel: move mask + step, {n} random reachable states per launch "
                                f"({bytes_per_launch / 1e6:.0f} MB per launch, larger than L2)"},
         "roofline": {"kernel": "rules_mask_step_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": gbs / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "frac": gbs / hbm_peak, "traffic": ncu_traffic("rules_mask_step_kernel", "rules"),
+                     "algorithmic_bytes_per_launch": bytes_per_launch,
                      "avg_launch_us": avg * 1e3, "min_launch_us": min(ms) * 1e3},
         "gpu_launches": a.steps, "clocks": clocks.summary()}), flush=True)
 

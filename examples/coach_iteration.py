@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""One full Coach iteration on the device (BASELINE config 5): batched self-play -> NNetWrapper.train (gradient
-all-reduce over NCCL when launched with torchrun) -> BatchedArena against Random and Greedy.
+"""One full Coach iteration on the device (BASELINE config 5): self-play sharded over the ranks -> NNetWrapper.train
+with the gradient all-reduce (NCCL under torchrun) -> BatchedArena against Random and Greedy, games sharded over the
+ranks and only the W/L/D counters all-reduced.
 
-    python examples/coach_iteration.py --games 256 --sims 25 --arena 20 --epochs 1
-    torchrun --nproc-per-node 8 examples/coach_iteration.py --games 4096 --sims 200 --arena 100
+    python examples/coach_iteration.py --games 32 --sims 25 --arena 20 --max-turns 40
+    torchrun --nproc-per-node 8 examples/coach_iteration.py --games 64 --sims 200 --arena 100
 """
 import argparse
 import os
@@ -18,19 +19,20 @@ import torch.distributed as dist
 
 import inflexion_b200  # noqa: F401
 from inflexion_b200.arena_batched import BatchedArena
+from inflexion_b200.Coach import Coach
 from inflexion_b200.inflexion.InflexionGame import InflexionGame
 from inflexion_b200.inflexion.pytorch import NNet as nnet_mod
-from inflexion_b200.selfplay import SelfPlayEngine
+from inflexion_b200.utils import dotdict
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--games", type=int, default=256, help="self-play games per GPU")
+    ap.add_argument("--games", type=int, default=32, help="self-play games per GPU")
     ap.add_argument("--sims", type=int, default=25)
     ap.add_argument("--max-turns", type=int, default=343)
     ap.add_argument("--arena", type=int, default=20)
     ap.add_argument("--epochs", type=int, default=1)
-    ap.add_argument("--max-moves", type=int, default=None, help="cut self-play after this many moves (smoke runs)")
+    ap.add_argument("--gather", action="store_true", help="all-gather the un-expanded self-play records (final example gather)")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -40,28 +42,33 @@ def main():
     game = InflexionGame(7, max_turns=a.max_turns, max_power=6)
     nnet_mod.args["epochs"] = a.epochs
     nnet = nnet_mod.NNetWrapper(game)
+    coach = Coach(game, nnet, dotdict({"numMCTSSims": a.sims, "cpuct": 1, "tempThreshold": 30, "numEps": a.games * world}))
 
     t0 = time.time()
-    eng = SelfPlayEngine(a.games, a.sims, nnet.predict_head, fused_head=True, temp_threshold=30, seed=1,
-                         max_turns=a.max_turns, game_id_base=rank * a.games)
-    moves = eng.play_episode(a.max_moves)
-    eng.mcts.raise_on_faults()
+    examples = coach.selfPlayBatch(a.games * world, seed=1, gather=a.gather)   # this rank's games (all games with --gather)
     torch.cuda.synchronize()
     t1 = time.time()
-    planes, pi, v = eng.examples(games=range(min(a.games, 8)))  # expand a few games' examples for the training step
-    examples = [(planes[i], pi[i].tolist(), float(v[i])) for i in range(len(v))]
+    moves = a.max_turns + 1
     if rank == 0:
-        print(f"self-play: {a.games * world} games x {moves} moves x {a.sims} sims in {t1 - t0:.1f}s "
-              f"({a.games * world * moves * a.sims / (t1 - t0):.3e} sims/s); {len(examples)} examples from {min(a.games, 8)} games")
-    if len(examples) >= nnet_mod.args.batch_size:
-        np.random.seed(rank)
-        hist = nnet.train(examples, verbose=False)              # rank-local examples, all-reduced gradients
+        print(f"self-play: {a.games * world} games x {moves} moves x {a.sims} sims on {world} GPU(s) in {t1 - t0:.1f}s "
+              f"({a.games * world * moves * a.sims / (t1 - t0):.3e} sims/s incl. example expansion); "
+              f"{len(examples)} examples on rank 0", flush=True)
+    np.random.seed(rank)                                        # every rank draws its own batches
+    hist = nnet.train(examples, verbose=False)                  # gradients all-reduced across ranks
+    w = torch.cat([p.detach().reshape(-1) for p in nnet.nnet.parameters()])
+    if world > 1:                                               # ranks must hold identical weights after training
+        ref = w.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, w), "ranks diverged"
+    if rank == 0:
+        print("train: loss_pi %.3f -> %.3f, loss_v %.3f -> %.3f (weights identical on all ranks)"
+              % (hist[0][0], hist[-1][0], hist[0][1], hist[-1][1]), flush=True)
+    for opp in ("random", "greedy"):
+        t2 = time.time()
+        one, two, dr = BatchedArena(nnet.predict_head, a.sims, opponent=opp, seed=2, max_turns=a.max_turns,
+                                    fused_head=True).playGames(a.arena)
         if rank == 0:
-            print("train: loss_pi %.3f -> %.3f, loss_v %.3f -> %.3f" % (hist[0][0], hist[-1][0], hist[0][1], hist[-1][1]))
-    if rank == 0:
-        for opp in ("random", "greedy"):
-            one, two, dr = BatchedArena(nnet.predict_batch, a.sims, opponent=opp, seed=2, max_turns=a.max_turns).playGames(a.arena)
-            print(f"arena vs {opp}: MCTS {one} / {opp} {two} / draws {dr}")
+            print(f"arena vs {opp}: MCTS {one} / {opp} {two} / draws {dr}  ({a.arena} games in {time.time() - t2:.1f}s)", flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

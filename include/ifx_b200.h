@@ -144,14 +144,15 @@ typedef struct ifx_mcts ifx_mcts;
 /* Offsets (bytes) of the SoA pools inside the workspace, for inspection by tests (MCTS tables
  * Qsa/Nsa/Ns/Ps of MCTS.py:25-31 are not read by any caller of the reference). */
 typedef struct ifx_mcts_layout {
-  int64_t rows;       /* float [G][C][3][352]: P, N word (count | child hint | kind; see ifx_tree.cuh), Q */
-  int64_t q64;        /* double [G][C][344]: Q when its kind is Python-float       */
+  int64_t rows;       /* float [G][C][3][352]: P, N word (count | child hint | kind; see ifx_tree.cuh), Q.
+                         COMPACT: entry i of a row belongs to the node's i-th valid action (ascending)    */
+  int64_t q64;        /* double [G][C][344]: Q when its kind is Python-float; compact */
   int64_t node_key;   /* uint64 [G][C][2]                                                               */
   int64_t node_head;  /* {int32 Ns, float sqrt(Ns), float sqrt(Ns+1e-8), pad} [G][C]                    */
   int64_t hash;       /* uint64 [G][H][2]                                                               */
   int64_t free_stack; /* uint16 [G][C]                                                                  */
   int64_t per_game;   /* struct per game, see csrc/ifx_tree.cuh                                         */
-  int64_t path;       /* uint32x4 [G][32]: {slot<<9|action, N word, Q bits, Ns} per path level           */
+  int64_t path;       /* uint32x4 [G][32]: {slot<<9|row entry, N word, Q bits, Ns} per path level        */
   int64_t roots;      /* ifx_state [G]                                                                  */
   int64_t leaves;     /* ifx_state [G]                                                                  */
   int64_t total;      /* == ifx_mcts_workspace_bytes                                                    */
@@ -222,6 +223,16 @@ IFX_API int ifx_mcts_status(ifx_mcts* m, int32_t* status, void* stream);
 IFX_API int ifx_mcts_get_roots(ifx_mcts* m, ifx_state* roots, void* stream);
 /* counters uint64 [4]: node visits V (expanded nodes traversed), expansions E, terminal leaves, simulations. */
 IFX_API int ifx_mcts_counters(ifx_mcts* m, uint64_t* counters, void* stream);
+
+/* ---- deterministic evaluator ------------------------------------------------------------------ */
+
+/* The deterministic policy/value stub of the parity contract ("visit counts bit-exact ... when both use a fixed
+ * deterministic net stub", BASELINE.json north_star) as one kernel: stubnet.py:stub_policy_value bit for bit.
+ * nn_in float32 [n][4][7][7] (the planes NNetWrapper.predict receives, NNet.py:78-94), coef int64 [196] (the stub's
+ * mixing coefficients), dyadic = 1 for integer priors / 0 for k/1000003 priors; pi float32 rows of pi_stride >= 343,
+ * v float32 [n].  Used by the bit-exact tests and by tree-and-rules-only throughput runs (bench.py --net stub). */
+IFX_API int ifx_stub_policy_value(const float* nn_in, int64_t n, const int64_t* coef, int dyadic, float* pi,
+                                  int64_t pi_stride, float* v, void* stream);
 
 #ifdef __cplusplus
 }

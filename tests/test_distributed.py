@@ -87,3 +87,46 @@ def test_data_parallel_training_keeps_ranks_in_sync(tmp_path):
     w0, w1 = torch.load(os.path.join(tmp_path, "weights.pt"))
     assert torch.equal(w0, w1)                               # identical updates from all-reduced gradients
     assert float(w0.abs().sum()) > 0
+
+
+def _coach_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import inflexion_b200  # noqa: F401
+    from hostsim import hostsim_backend
+    from inflexion_b200.arena_batched import BatchedArena
+    from inflexion_b200.selfplay import SelfPlayEngine, build_examples
+    from inflexion_b200.stubnet import stub_policy_value
+    be = hostsim_backend()
+    # sharded Arena: 6 games over 2 ranks, only the W/L/D counters are all-reduced
+    res = BatchedArena(lambda x: stub_policy_value(x), 6, opponent="greedy", seed=4, max_turns=8, backend=be).playGames(6)
+    # final example gather: un-expanded records of both ranks, expanded after the gather
+    per_rank = 2
+    eng = SelfPlayEngine(per_rank, 8, lambda x: stub_policy_value(x), temp_threshold=3, seed=5, max_turns=5,
+                         game_id_base=rank * per_rank, backend=be)
+    while eng.move < eng.max_moves:
+        eng.play_move()
+    planes, pi, v = build_examples(be, eng.gather_records())
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "coach.npz"), res=np.asarray(res), planes=planes, pi=pi, v=v)
+    dist.destroy_process_group()
+
+
+def test_sharded_arena_and_example_gather(tmp_path):
+    port = _free_port()
+    mp.spawn(_coach_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(os.path.join(tmp_path, "coach.npz"))
+    from hostsim import hostsim_backend
+    from inflexion_b200.arena_batched import BatchedArena
+    from inflexion_b200.selfplay import SelfPlayEngine
+    from inflexion_b200.stubnet import stub_policy_value
+    be = hostsim_backend()
+    single = BatchedArena(lambda x: stub_policy_value(x), 6, opponent="greedy", seed=4, max_turns=8, backend=be).playGames(6)
+    assert tuple(got["res"]) == single and sum(single) == 6
+    eng = SelfPlayEngine(4, 8, lambda x: stub_policy_value(x), temp_threshold=3, seed=5, max_turns=5, backend=be)
+    while eng.move < eng.max_moves:
+        eng.play_move()
+    planes, pi, v = eng.examples()
+    assert len(v) > 0 and np.array_equal(got["planes"], planes) and np.array_equal(got["pi"], pi) and np.array_equal(got["v"], v)

@@ -232,3 +232,20 @@ def test_terminal_budget_does_not_change_the_search(backend):
         else:
             for (c0, q0, a0), (c1, q1, a1) in zip(ref, out):
                 assert np.array_equal(c0, c1) and q0.tobytes() == q1.tobytes() and np.array_equal(a0, a1)
+
+
+@pytest.mark.parametrize("mode", ["float", "dyadic"])
+def test_stub_kernel_equals_torch_stub(backend, mode):
+    """csrc/ifx_stub.cu is stubnet.stub_policy_value bit for bit (it is the evaluator of tree-only throughput runs)."""
+    from inflexion_b200.stubnet import stub_kernel_evaluator
+    G = 37
+    m = BatchedMCTS(G, 4, 1.0, seed=2, backend=backend)
+    rng = np.random.default_rng(5)
+    x = np.zeros((G, 4, 49), dtype=np.float32)
+    own = rng.random((G, 49)) < 0.3
+    x[:, 0] = own; x[:, 1] = (rng.random((G, 49)) < 0.3) & ~own
+    x[:, 2] = rng.integers(0, 344, G)[:, None]; x[:, 3] = rng.integers(0, 2, G)[:, None]
+    nn_in = torch.from_numpy(x.reshape(G, 4, 7, 7)).to(backend.device)
+    pi, v = stub_kernel_evaluator(m, mode)(nn_in)
+    pi_ref, v_ref = stub_policy_value(nn_in, mode)
+    assert torch.equal(pi.cpu(), pi_ref.cpu()) and torch.equal(v.cpu(), v_ref.cpu())

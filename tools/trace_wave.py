@@ -10,14 +10,16 @@ from inflexion_b200.stubnet import stub_policy_value
 games = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 net = sys.argv[2] if len(sys.argv) > 2 else "stub"
 be = Backend.cuda(0)
-if net == "default":
+if net.startswith("default"):
     from inflexion_b200.inflexion.InflexionGame import InflexionGame
     from inflexion_b200.inflexion.pytorch.NNet import NNetWrapper
     torch.manual_seed(0); torch.backends.cudnn.benchmark = True
-    evaluate = NNetWrapper(InflexionGame(7, max_turns=343, max_power=6), device=be.device).predict_batch
+    nn = NNetWrapper(InflexionGame(7, max_turns=343, max_power=6), device=be.device)
+    fused = net == "default"                  # "default" = the bench configuration (binary16 head fused into the tree kernel)
+    evaluate = nn.predict_head if fused else nn.predict_batch     # "default-exact": float32 pi / v, exact renormalisation
 else:
-    evaluate = lambda x: stub_policy_value(x)
-eng = SelfPlayEngine(games, 100, evaluate, seed=2023, record=False, use_graph=False, backend=be)
+    evaluate, fused = (lambda x: stub_policy_value(x)), False
+eng = SelfPlayEngine(games, 100, evaluate, seed=2023, record=False, use_graph=False, backend=be, fused_head=fused)
 for _ in range(4):
     eng.play_move()
 dbg = torch.zeros((games, 8), dtype=torch.int64, device=be.device)
