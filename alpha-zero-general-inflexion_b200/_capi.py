@@ -19,7 +19,8 @@ c_void_p, c_int, c_int32, c_int64, c_size_t, c_float, c_uint64 = (
 class MctsConfig(C.Structure):
     _fields_ = [("n_games", c_int32), ("nodes_per_game", c_int32), ("hash_per_game", c_int32),
                 ("max_depth", c_int32), ("num_sims", c_int32), ("cpuct", c_float), ("seed", c_uint64),
-                ("policy_is_logits", c_int32), ("terminal_sims_per_wave", c_int32)]
+                ("policy_is_logits", c_int32), ("terminal_sims_per_wave", c_int32),
+                ("dirichlet_alpha", c_float), ("dirichlet_eps", c_float)]
 
 
 class MctsLayout(C.Structure):

@@ -72,18 +72,24 @@ static inline float ifx_h2f(uint16_t h) {
   float f; memcpy(&f, &bits, 4); return f;
 }
 static inline float ifx_expf(float x) { return expf(x); }
-static inline float ifx_fast_expf(float x) { return expf(x); }
+static inline float ifx_fast_exp2f(float x) { return exp2f(x); }
 static inline float ifx_frcp(float x) { return 1.0f / x; }
 static inline float ifx_logf(float x) { return logf(x); }
 static inline float ifx_tanhf(float x) { return tanhf(x); }
+static inline float ifx_cosf(float x) { return cosf(x); }
+static inline float ifx_powf(float x, float y) { return powf(x, y); }
 #else
 #include <cuda_fp16.h>
 IFX_D float ifx_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 IFX_D float ifx_expf(float x) { return expf(x); }
-IFX_D float ifx_fast_expf(float x) { return __expf(x); }        // FMUL + MUFU.EX2 (2 ulp); fused-head path only
+IFX_D float ifx_fast_exp2f(float x) {                           // one MUFU.EX2 (2 ulp, flush-to-zero); fused-head path only
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
 IFX_D float ifx_frcp(float x) { return __frcp_rn(x); }
 IFX_D float ifx_logf(float x) { return logf(x); }
 IFX_D float ifx_tanhf(float x) { return tanhf(x); }
+IFX_D float ifx_cosf(float x) { return cosf(x); }
+IFX_D float ifx_powf(float x, float y) { return powf(x, y); }
 #endif
 
 // ---------------------------------------------------------------------------------------------

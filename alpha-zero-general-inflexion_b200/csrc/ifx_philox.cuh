@@ -8,6 +8,9 @@
 #define IFX_RNG_TIEBREAK 1u   // MCTS.py:53: index = w0 % number_of_ties
 #define IFX_RNG_ACTION 2u     // Coach.py:81: u = ((w0>>5)*2^26 + (w1>>6)) / 2^53
 
+//      purpose 3u            // RandomPlayer (csrc/ifx_rules_api.cu)
+#define IFX_RNG_DIRICHLET 4u  // optional root noise (not in the reference): gamma variates, see tree_root_noise
+
 struct IfxRand4 { uint32_t w[4]; };
 
 IFX_HD IfxRand4 ifx_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {

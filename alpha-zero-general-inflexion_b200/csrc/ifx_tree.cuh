@@ -76,18 +76,20 @@ IFX_HD int ifx_valid_below(const ValidSet& V, int a) {
   if (m == IFX_SPAWN) return 6 * V.n_own + ifx_rank64(V.spawn, cell);
   return V.nv;
 }
-#ifdef IFX_HOSTSIM
-static inline int ifx_nth_set_bit64(uint64_t m, int k) {      // position of the k-th (0-based) set bit
-  for (int i = 0; i < 64; ++i) if ((m >> i) & 1ull) { if (k == 0) return i; --k; }
-  return 64;
+// position of the k-th (0-based) set bit of m (k < popc(m)): a six-step binary search on population counts
+// (__fns is a software loop on this architecture, ~10x the instructions)
+IFX_HD int ifx_nth_set_bit64(uint64_t m, int k) {
+  int pos = 0;
+  uint32_t w = (uint32_t)m;
+  int c = ifx_popc32(w);
+  if (k >= c) { k -= c; pos = 32; w = (uint32_t)(m >> 32); }
+  c = ifx_popc32(w & 0xFFFFu); if (k >= c) { k -= c; pos += 16; w >>= 16; }
+  c = ifx_popc32(w & 0xFFu);   if (k >= c) { k -= c; pos += 8;  w >>= 8; }
+  c = ifx_popc32(w & 0xFu);    if (k >= c) { k -= c; pos += 4;  w >>= 4; }
+  c = ifx_popc32(w & 0x3u);    if (k >= c) { k -= c; pos += 2;  w >>= 2; }
+  c = (int)(w & 1u);           if (k >= c) { pos += 1; }
+  return pos;
 }
-#else
-IFX_D int ifx_nth_set_bit64(uint64_t m, int k) {
-  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-  const int c = __popc(lo);
-  return k < c ? (int)__fns(lo, 0u, k + 1) : 32 + (int)__fns(hi, 0u, k - c + 1);
-}
-#endif
 // action index of compact entry ci (0 <= ci < nv)
 IFX_HD int ifx_compact_to_action(const ValidSet& V, int ci) {
   const int spread = 6 * V.n_own;
@@ -123,6 +125,7 @@ struct TreeParams {
   ifx_state* roots;     // [G]
   ifx_state* leaves;    // [G]
   int32_t G, C, H, maxd, num_sims, logits, term_budget;
+  float dir_alpha, dir_eps;   // optional Dirichlet root noise (eps = 0: off = the reference's behaviour)
   uint64_t* debug;      // optional [G][8]: ns stamps {start, loads done, expanded, backed up, first level done, end}, depth, probes
   float cpuct;
   uint64_t seed;
@@ -168,23 +171,30 @@ IFX_HD uint32_t tree_valid4(uint64_t own, uint64_t spawn, int a) {
 }
 
 // ---- hash (open addressing, linear probing, never deleted from: rebuilt when nodes are reclaimed) ----
-// The first group of 32 entries is requested by tree_hash_issue; the caller may do unrelated work before
-// tree_hash_resolve consumes it (and keeps probing in the rare case the first group decides nothing).
+// Entries are probed IFX_PROBE at a time (8 x 16 B = one 128-byte line; at a load factor <= 0.5 the first group
+// almost always holds the match or an empty entry).  The first group is requested by tree_hash_issue; the caller
+// may do unrelated work before tree_hash_resolve consumes it (and keeps probing if that group decides nothing).
 // resolve returns the slot, or -1 with *miss_pos = position of the first empty entry of the probe sequence
 // (the insert point).
+#define IFX_PROBE 8
 IFX_D void tree_hash_issue(const TreeParams& P, int g, uint32_t h, LaneVar<IfxKey>& first) {
   const IfxKey* tab = P.hash + (int64_t)g * P.H;
-  IFX_FOR_LANES(l) { first[l] = tab[(h + l) & (P.H - 1)]; }
+  IFX_FOR_LANES(l) {
+    IfxKey e; e.k0 = 0; e.k1 = 0;                            // lanes beyond the group: neither a match nor empty
+    if (l < IFX_PROBE) e = tab[(h + l) & (P.H - 1)];
+    first[l] = e;
+  }
 }
 IFX_D int tree_hash_resolve(const TreeParams& P, int g, uint64_t k0, uint64_t k1, uint32_t h, const LaneVar<IfxKey>& first,
                             int* miss_pos) {
   const IfxKey* tab = P.hash + (int64_t)g * P.H;
-  for (int probe = 0; probe < P.H; probe += 32) {
+  for (int probe = 0; probe < P.H; probe += IFX_PROBE) {
     LaneVar<int> match, empty, slot;
     IFX_FOR_LANES(l) {
-      const IfxKey e = probe == 0 ? first[l] : tab[(h + probe + l) & (P.H - 1)];
-      match[l] = (e.k0 == k0 && (e.k1 & IFX_KEY1_MASK) == k1) ? 1 : 0;
-      empty[l] = e.k0 == IFX_KEY_EMPTY ? 1 : 0;
+      IfxKey e = first[l];
+      if (probe > 0) { e.k0 = 0; e.k1 = 0; if (l < IFX_PROBE) e = tab[(h + probe + l) & (P.H - 1)]; }
+      match[l] = (l < IFX_PROBE && e.k0 == k0 && (e.k1 & IFX_KEY1_MASK) == k1) ? 1 : 0;
+      empty[l] = (l < IFX_PROBE && e.k0 == IFX_KEY_EMPTY) ? 1 : 0;
       slot[l] = (int)(e.k1 >> 50);
     }
     const uint32_t mm = lanes_ballot(match), me = lanes_ballot(empty);
@@ -442,8 +452,10 @@ IFX_D float tree_head_exp(const uint16_t* head, PolicyRegs& R) {
       const int i = 4 * l + 128 * j;
       IfxF4 v = R.p[j][l];
       if (i == 340) val[l] = ifx_tanhf(v.w);                                // lane 21, j = 2 holds element 343
-      v.x = i < IFX_ACTIONS ? ifx_fast_expf(v.x - m) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_fast_expf(v.y - m) : 0.0f;
-      v.z = i + 2 < IFX_ACTIONS ? ifx_fast_expf(v.z - m) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_fast_expf(v.w - m) : 0.0f;
+      // exp(x - m) = 2^((x - m) * log2(e)): one multiply-add and one MUFU.EX2 per prior
+      const float L2E = 1.4426950408889634f, mb = -m * L2E;
+      v.x = i < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.x, L2E, mb)) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.y, L2E, mb)) : 0.0f;
+      v.z = i + 2 < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.z, L2E, mb)) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.w, L2E, mb)) : 0.0f;
       R.p[j][l] = v;
     }
   }
@@ -540,6 +552,44 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
   return slot;
 }
 
+// ---- optional Dirichlet root noise (NOT in the reference; off unless dirichlet_eps > 0) ----
+// P(root, .) <- (1 - eps) P + eps * Dir(alpha) over the root's valid actions, once per move, on the device:
+// gamma(alpha) variates by Marsaglia-Tsang on alpha + 1 with the U^(1/alpha) boost, every uniform a Philox value
+// keyed by (seed; game, move, entry | attempt << 16, IFX_RNG_DIRICHLET), normalised across the warp.
+IFX_HD float ifx_u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
+IFX_HD float tree_gamma(uint64_t seed, uint32_t game, uint32_t move, uint32_t entry, float alpha) {
+  const float d = (alpha + 1.0f) - (1.0f / 3.0f), c = 1.0f / ifx_fsqrt(9.0f * d);
+  float g = d;                                              // (fallback after 8 rejections: the mode region)
+  float boost_u = 0.5f;
+  for (uint32_t attempt = 0; attempt < 8u; ++attempt) {
+    const IfxRand4 r = ifx_philox(seed, game, move, entry | (attempt << 16), IFX_RNG_DIRICHLET);
+    if (attempt == 0u) boost_u = ifx_u01(r.w[3]);
+    const float x = ifx_fsqrt(-2.0f * ifx_logf(ifx_u01(r.w[0]))) * ifx_cosf(6.2831853071795865f * ifx_u01(r.w[1]));
+    const float t = 1.0f + c * x, v = t * t * t;
+    if (v > 0.0f && ifx_logf(ifx_u01(r.w[2])) < 0.5f * x * x + d - d * v + d * ifx_logf(v)) { g = d * v; break; }
+  }
+  return g * ifx_powf(boost_u, 1.0f / alpha);
+}
+IFX_D void tree_root_noise(const TreeParams& P, int g, const IfxGame& G, int slot, int nv) {
+  if (!(P.dir_eps > 0.0f) || slot < 0 || nv <= 0) return;
+  float* prow = tree_row(P, g, slot, 0);
+  LaneVar<float> part;
+  IFX_FOR_LANES(l) {
+    float s = 0.0f;
+    for (int i = l; i < nv; i += 32) s += tree_gamma(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)i, P.dir_alpha);
+    part[l] = s;
+  }
+  const float total = lanes_sum_f32(part);
+  if (!(total > 0.0f)) return;
+  IFX_FOR_LANES(l) {
+    for (int i = l; i < nv; i += 32) {
+      const float eta = tree_gamma(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)i, P.dir_alpha) / total;
+      prow[i] = (1.0f - P.dir_eps) * prow[i] + P.dir_eps * eta;
+    }
+  }
+  IFX_SYNCWARP();
+}
+
 // random_symmetry of (game, move, sim): k + 6*shift + 42*axis (InflexionGame.py:115-122; MCTS.py:90-92)
 IFX_D int tree_draw_symmetry(const TreeParams& P, const IfxGame& G) {
   const IfxRand4 r = ifx_philox(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)G.sims_done, IFX_RNG_SYMMETRY);
@@ -615,7 +665,16 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     tree_policy_load(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, pol);
   }
   LaneVar<IfxU4> path;
-  IFX_FOR_LANES(l) { path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
+  // the first 8 levels of the pending leaf's path travel with the first round trip (one 128-byte line); deeper
+  // paths (rare) fetch the rest once the record says so
+  IFX_FOR_LANES(l) {
+    IfxU4 e = {0u, 0u, 0u, 0u};
+    if (l < 8) e = P.path[(int64_t)g * IFX_MAX_DEPTH + l];
+    path[l] = e;
+  }
+  if (G.pending && G.path_len > 8) {
+    IFX_FOR_LANES(l) { if (l >= 8) path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
+  }
   if (G.faults) { if (mirror_slot >= 0) tree_mirror_wait(); return; }
   if (DBG) dbg_t1 = ifx_now_ns() + (uint64_t)(G.pending & 0) + (uint64_t)(leaf.turn & 0);
   if (G.pending) {
@@ -624,7 +683,10 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     if (DBG) dbg_t2 = ifx_now_ns();
     if (mirror_slot >= 0) tree_mirror_wait();               // the backup patches the mirror: it must have landed
     if (slot >= 0) {
-      if (G.path_len == 0) { G.root_slot = slot; G.root_nv = leaf_nv; }   // the root itself was the leaf
+      if (G.path_len == 0) {                                // the root itself was the leaf
+        G.root_slot = slot; G.root_nv = leaf_nv;
+        tree_root_noise(P, g, G, slot, leaf_nv);            // (no-op unless dirichlet_eps > 0)
+      }
       // search() of the leaf returns -v, v a float32 (MCTS.py:112; NNet.py:94)
       tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot, mirror_slot >= 0 ? mirror : nullptr);
       G.sims_done += 1; G.n_sims += 1;
@@ -800,6 +862,7 @@ IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
   G.path_len = 0;
   G.leaf_hpos = -1;
   G.sims_done = root.outcome == IFX_ONGOING ? 0 : P.num_sims;   // a finished game is never searched
+  if (root.outcome == IFX_ONGOING) tree_root_noise(P, g, G, root_slot, G.root_nv);   // (no-op unless dirichlet_eps > 0)
   if (IFX_LANE0) P.games[g] = G;
 }
 

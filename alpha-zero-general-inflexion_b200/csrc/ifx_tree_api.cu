@@ -29,6 +29,7 @@ static int check_cfg(const ifx_mcts_config* c) {
   if (c->max_depth < 1 || c->max_depth > IFX_MAX_DEPTH || c->num_sims < 0) return IFX_E_ARG;
   if (c->policy_is_logits != 0 && c->policy_is_logits != 2) return IFX_E_ARG;
   if (c->terminal_sims_per_wave < 0) return IFX_E_ARG;
+  if (c->dirichlet_eps < 0.0f || c->dirichlet_eps > 1.0f || (c->dirichlet_eps > 0.0f && !(c->dirichlet_alpha > 0.0f))) return IFX_E_ARG;
   return IFX_OK;
 }
 
@@ -247,7 +248,8 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   P.free_stack = (uint16_t*)(b + L.free_stack); P.games = (IfxGame*)(b + L.per_game);
   P.path = (IfxU4*)(b + L.path); P.roots = (ifx_state*)(b + L.roots); P.leaves = (ifx_state*)(b + L.leaves);
   P.G = c->n_games; P.C = c->nodes_per_game; P.H = c->hash_per_game; P.maxd = c->max_depth;
-  P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.term_budget = c->terminal_sims_per_wave; P.cpuct = c->cpuct; P.seed = c->seed;
+  P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.term_budget = c->terminal_sims_per_wave;
+  P.dir_alpha = c->dirichlet_alpha; P.dir_eps = c->dirichlet_eps; P.cpuct = c->cpuct; P.seed = c->seed;
   P.debug = nullptr;
 #ifndef IFX_HOSTSIM
   // one warp per CTA, ~6 KB of shared memory each: ask for the largest shared-memory carve-out so that the

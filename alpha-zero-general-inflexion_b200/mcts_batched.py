@@ -32,11 +32,14 @@ def default_pool_size(num_sims: int) -> int:
 class BatchedMCTS:
     def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | None = None,
                  max_depth: int = 32, backend: Backend | None = None, fused_head: bool = False,
-                 pad_policy_rows: bool = True, terminal_sims_per_wave: int = 1):
+                 pad_policy_rows: bool = True, terminal_sims_per_wave: int = 1, dirichlet_alpha: float = 0.0,
+                 dirichlet_eps: float = 0.0):
         """fused_head: the net hands over its last GEMM output (float16 [G,344]: 343 policy logits + the value
         pre-activation, buffer ``nn_head``) and the tree kernel applies softmax / tanh itself.
         terminal_sims_per_wave: how many simulations that end in a terminal state (no net needed) a game may run in
-        one wave before it yields (0 = no limit); results do not depend on it, the length of a wave's tail does."""
+        one wave before it yields (0 = no limit); results do not depend on it, the length of a wave's tail does.
+        dirichlet_alpha / dirichlet_eps: optional root noise P <- (1-eps) P + eps Dir(alpha), drawn on the device once
+        per move.  The reference's MCTS has none, so the default (eps = 0) is off and the bit-exact parity holds."""
         self.be = backend or default_backend()
         self.n_games, self.num_sims = int(n_games), int(num_sims)
         nodes = int(nodes_per_game or default_pool_size(num_sims))
@@ -47,7 +50,8 @@ class BatchedMCTS:
         self.cfg = _capi.MctsConfig(n_games=self.n_games, nodes_per_game=nodes, hash_per_game=hash_slots,
                                     max_depth=max_depth, num_sims=self.num_sims, cpuct=float(np.float32(cpuct)),
                                     seed=int(seed) & (2 ** 64 - 1), policy_is_logits=2 if fused_head else 0,
-                                    terminal_sims_per_wave=int(terminal_sims_per_wave))
+                                    terminal_sims_per_wave=int(terminal_sims_per_wave),
+                                    dirichlet_alpha=float(dirichlet_alpha), dirichlet_eps=float(dirichlet_eps))
         dll = self.be.dll
         self.layout = _capi.MctsLayout()
         self.be.check(dll.ifx_mcts_get_layout(C.byref(self.cfg), C.byref(self.layout)))

@@ -27,7 +27,7 @@ class SelfPlayEngine:
                  max_turns: int = 343, game_id_base: int = 0, nodes_per_game: int | None = None,
                  record: bool = True, use_graph: bool | None = None, backend: Backend | None = None,
                  fused_head: bool = False, auto_restart: bool = False, restart_stride: int | None = None,
-                 record_moves: int | None = None):
+                 record_moves: int | None = None, dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.0):
         """evaluate(nn_in f32 [G,4,7,7]) -> (pi f32 [G,343], v f32 [G]) on the device (e.g. nnet.predict_batch); with
         ``fused_head`` it is evaluate(nn_in, out f16 [G,344]) writing the raw head output (e.g. nnet.predict_head) and
         the tree kernel does the softmax / tanh.  ``auto_restart``: a game that ends starts its next episode at once
@@ -38,7 +38,7 @@ class SelfPlayEngine:
         self.max_turns, self.game_id_base = int(max_turns), int(game_id_base)
         self.evaluate = evaluate
         self.mcts = BatchedMCTS(self.G, num_sims, cpuct, seed=seed, nodes_per_game=nodes_per_game, backend=self.be,
-                                fused_head=fused_head)
+                                fused_head=fused_head, dirichlet_alpha=dirichlet_alpha, dirichlet_eps=dirichlet_eps)
         self.record = record
         # a game lasts at most max_turns+1 moves; continuous play (auto_restart) records up to ``record_moves`` moves
         self.max_moves = int(record_moves or self.max_turns + 1)

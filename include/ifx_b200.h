@@ -137,6 +137,9 @@ typedef struct ifx_mcts_config {
                                child is a won position would otherwise run ALL its remaining simulations inside one
                                launch while the other warps have long finished (the tail of the wave).  Results do
                                not depend on T; num_sims+1 waves still complete a move (see ifx_mcts_wave)            */
+  float dirichlet_alpha;    /* optional root noise, NOT part of the reference (its MCTS has none): when            */
+  float dirichlet_eps;      /* dirichlet_eps > 0, P(root,.) <- (1-eps) P + eps Dir(alpha) over the valid actions,
+                               once per move, drawn on the device from Philox.  0 (default) = reference behaviour   */
 } ifx_mcts_config;
 
 typedef struct ifx_mcts ifx_mcts;

@@ -249,3 +249,42 @@ def test_stub_kernel_equals_torch_stub(backend, mode):
     pi, v = stub_kernel_evaluator(m, mode)(nn_in)
     pi_ref, v_ref = stub_policy_value(nn_in, mode)
     assert torch.equal(pi.cpu(), pi_ref.cpu()) and torch.equal(v.cpu(), v_ref.cpu())
+
+
+def test_optional_dirichlet_root_noise(backend):
+    """Not in the reference (default off).  With dirichlet_eps > 0 the root priors become (1-eps) P + eps eta,
+    eta ~ Dir(alpha) over the valid actions, once per move: eta >= 0, sums to 1, has the Dirichlet mean and variance
+    across games; the search stays deterministic in the seed; eps = 0 leaves everything bit-identical."""
+    G, sims, alpha, eps = 96, 6, 0.3, 0.25
+
+    def run(**kw):
+        m = BatchedMCTS(G, sims, 1.0, seed=13, backend=backend, **kw)
+        m.reset(start_states(G, 343))
+        m.search(stub_eval("float"))
+        m.raise_on_faults()
+        tv = m.table_views()
+        roots = []
+        for g in range(G):                                   # the root is the node whose turn is 0
+            used = np.nonzero(tv["key"][g, :, 0] != np.uint64(2 ** 64 - 1))[0]
+            slot = [s for s in used if int(tv["key"][g, s, 0]) >> 49 == 0][0]
+            roots.append(tv["P"][g, slot].copy())
+        return np.stack(roots), m.root_stats()["counts"].cpu().numpy()
+    p0, c0 = run()
+    p0b, c0b = run(dirichlet_alpha=alpha, dirichlet_eps=0.0)
+    assert p0.tobytes() == p0b.tobytes() and np.array_equal(c0, c0b)
+    p1, c1 = run(dirichlet_alpha=alpha, dirichlet_eps=eps)
+    p1b, c1b = run(dirichlet_alpha=alpha, dirichlet_eps=eps)
+    assert p1.tobytes() == p1b.tobytes() and np.array_equal(c1, c1b)        # deterministic in the seed
+    assert not np.array_equal(c0, c1)                                        # and it does change the search
+    valid = p0 > 0                                                           # start position: the 49 spawn moves
+    nv = valid.sum(axis=1)
+    assert np.all(nv == 49)
+    eta = (p1.astype(np.float64) - (1 - eps) * p0) / eps
+    assert np.all(eta[valid] > -1e-5) and np.all(eta[~valid] == 0)
+    assert np.allclose(eta.sum(axis=1), 1.0, atol=1e-4) and np.allclose(p1.sum(axis=1), 1.0, atol=1e-4)
+    e = eta[valid].reshape(G, 49)
+    var_theory = (1 / 49) * (1 - 1 / 49) / (49 * alpha + 1)
+    assert abs(e.mean() - 1 / 49) < 1e-6                                     # rows sum to one
+    assert 0.75 * var_theory < e.var() < 1.3 * var_theory, (e.var(), var_theory)
+    # different games draw different noise
+    assert len({e[g].tobytes() for g in range(G)}) == G
