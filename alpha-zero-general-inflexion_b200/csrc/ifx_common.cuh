@@ -14,6 +14,7 @@
 #ifdef IFX_HOSTSIM
   #define IFX_HD static inline
   #define IFX_D static inline
+  #define IFX_D_NOINLINE static
   #define IFX_LANE0 true
   #define IFX_FOR_LANES(lane) for (int lane = 0; lane < 32; ++lane)
   #define IFX_SYNCWARP() do {} while (0)
@@ -33,6 +34,7 @@
   #include <cuda_runtime.h>
   #define IFX_HD __device__ __forceinline__
   #define IFX_D __device__ __forceinline__
+  #define IFX_D_NOINLINE __device__ __noinline__   // rare paths kept out of the hot kernel's register allocation
   #define IFX_LANE0 ((threadIdx.x & 31u) == 0u)
   #define IFX_FOR_LANES(lane) for (int lane = (int)(threadIdx.x & 31u), _ifx_once = 1; _ifx_once; _ifx_once = 0)
   #define IFX_SYNCWARP() __syncwarp()
@@ -78,6 +80,7 @@ static inline float ifx_logf(float x) { return logf(x); }
 static inline float ifx_tanhf(float x) { return tanhf(x); }
 static inline float ifx_cosf(float x) { return cosf(x); }
 static inline float ifx_powf(float x, float y) { return powf(x, y); }
+static inline float ifx_noise_logf(float x) { return logf(x); }
 #else
 #include <cuda_fp16.h>
 IFX_D float ifx_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
@@ -88,8 +91,10 @@ IFX_D float ifx_fast_exp2f(float x) {                           // one MUFU.EX2 
 IFX_D float ifx_frcp(float x) { return __frcp_rn(x); }
 IFX_D float ifx_logf(float x) { return logf(x); }
 IFX_D float ifx_tanhf(float x) { return tanhf(x); }
-IFX_D float ifx_cosf(float x) { return cosf(x); }
-IFX_D float ifx_powf(float x, float y) { return powf(x, y); }
+// noise-only helpers: the fast intrinsics (no slow paths, no local memory); their accuracy is ample for a random draw
+IFX_D float ifx_cosf(float x) { return __cosf(x); }
+IFX_D float ifx_powf(float x, float y) { return __powf(x, y); }
+IFX_D float ifx_noise_logf(float x) { return __logf(x); }
 #endif
 
 // ---------------------------------------------------------------------------------------------

@@ -564,30 +564,33 @@ IFX_HD float tree_gamma(uint64_t seed, uint32_t game, uint32_t move, uint32_t en
   for (uint32_t attempt = 0; attempt < 8u; ++attempt) {
     const IfxRand4 r = ifx_philox(seed, game, move, entry | (attempt << 16), IFX_RNG_DIRICHLET);
     if (attempt == 0u) boost_u = ifx_u01(r.w[3]);
-    const float x = ifx_fsqrt(-2.0f * ifx_logf(ifx_u01(r.w[0]))) * ifx_cosf(6.2831853071795865f * ifx_u01(r.w[1]));
+    const float x = ifx_fsqrt(-2.0f * ifx_noise_logf(ifx_u01(r.w[0]))) * ifx_cosf(6.2831853071795865f * ifx_u01(r.w[1]));
     const float t = 1.0f + c * x, v = t * t * t;
-    if (v > 0.0f && ifx_logf(ifx_u01(r.w[2])) < 0.5f * x * x + d - d * v + d * ifx_logf(v)) { g = d * v; break; }
+    if (v > 0.0f && ifx_noise_logf(ifx_u01(r.w[2])) < 0.5f * x * x + d - d * v + d * ifx_noise_logf(v)) { g = d * v; break; }
   }
   return g * ifx_powf(boost_u, 1.0f / alpha);
 }
-IFX_D void tree_root_noise(const TreeParams& P, int g, const IfxGame& G, int slot, int nv) {
-  if (!(P.dir_eps > 0.0f) || slot < 0 || nv <= 0) return;
-  float* prow = tree_row(P, g, slot, 0);
+IFX_D_NOINLINE void tree_root_noise_apply(float* prow, uint64_t seed, uint32_t game, uint32_t move, int nv, float alpha, float eps) {
   LaneVar<float> part;
   IFX_FOR_LANES(l) {
     float s = 0.0f;
-    for (int i = l; i < nv; i += 32) s += tree_gamma(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)i, P.dir_alpha);
+    for (int i = l; i < nv; i += 32) s += tree_gamma(seed, game, move, (uint32_t)i, alpha);
     part[l] = s;
   }
   const float total = lanes_sum_f32(part);
   if (!(total > 0.0f)) return;
   IFX_FOR_LANES(l) {
     for (int i = l; i < nv; i += 32) {
-      const float eta = tree_gamma(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)i, P.dir_alpha) / total;
-      prow[i] = (1.0f - P.dir_eps) * prow[i] + P.dir_eps * eta;
+      const float eta = tree_gamma(seed, game, move, (uint32_t)i, alpha) / total;
+      prow[i] = (1.0f - eps) * prow[i] + eps * eta;
     }
   }
   IFX_SYNCWARP();
+}
+
+IFX_D void tree_root_noise(const TreeParams& P, int g, const IfxGame& G, int slot, int nv) {
+  if (!(P.dir_eps > 0.0f) || slot < 0 || nv <= 0) return;
+  tree_root_noise_apply(tree_row(P, g, slot, 0), P.seed, G.game_id, (uint32_t)G.move_idx, nv, P.dir_alpha, P.dir_eps);
 }
 
 // random_symmetry of (game, move, sim): k + 6*shift + 42*axis (InflexionGame.py:115-122; MCTS.py:90-92)
