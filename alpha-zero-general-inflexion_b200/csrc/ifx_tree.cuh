@@ -23,7 +23,8 @@ struct alignas(16) IfxGame {       // 64 bytes per game
   int32_t pending;                 // 1: `leaf` waits for the net
   int32_t faults;                  // IFX_F_* bits
   int32_t move_idx;                // getActionProb calls so far (RNG coordinate)
-  int32_t path_len;                // edges on the path to the pending leaf
+  int16_t path_len;                // edges on the path to the pending leaf
+  int16_t noise_due;               // 1: the root was expanded in the last wave and still waits for its Dirichlet noise
   int32_t free_top;                // free slots left on the stack (not counting next_slot)
   uint32_t game_id;                // RNG stream coordinate
   int32_t n_live;
@@ -688,7 +689,9 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     if (slot >= 0) {
       if (G.path_len == 0) {                                // the root itself was the leaf
         G.root_slot = slot; G.root_nv = leaf_nv;
-        tree_root_noise(P, g, G, slot, leaf_nv);            // (no-op unless dirichlet_eps > 0)
+        // optional root noise (off in the reference): the game yields, tree_noise_kernel perturbs the new root's
+        // priors before the next wave selects from them
+        if (P.dir_eps > 0.0f) G.noise_due = 1;
       }
       // search() of the leaf returns -v, v a float32 (MCTS.py:112; NNet.py:94)
       tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot, mirror_slot >= 0 ? mirror : nullptr);
@@ -700,7 +703,7 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     tree_mirror_wait();
   }
   int term_left = P.term_budget > 0 ? P.term_budget : 0x7fffffff;
-  while (!G.faults && G.sims_done < P.num_sims && term_left > 0) {
+  while (!G.faults && G.sims_done < P.num_sims && term_left > 0 && !G.noise_due) {
     ifx_state st = P.roots[g];                              // re-read per simulation (an L1/L2 hit) instead of sixteen
     int depth = 0;                                          // registers held across the whole wave
     int slot = G.root_slot;                                 // -1: the root is not expanded yet
@@ -744,7 +747,7 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
           if (IFX_LANE0) P.leaves[g] = st;
           IFX_FOR_LANES(l) { if (l < depth) P.path[(int64_t)g * IFX_MAX_DEPTH + l] = path[l]; }
           tree_write_nn_input(st, sym_src, nn_in);
-          G.path_len = depth; G.pending = 1; G.leaf_hpos = miss_pos;
+          G.path_len = (int16_t)depth; G.pending = 1; G.leaf_hpos = miss_pos;
           break;
         }
       }
@@ -863,6 +866,7 @@ IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
   G.root_nv = ifx_valid_set(ifx_own(root), ifx_spawn_mask(root)).nv;
   G.pending = 0;
   G.path_len = 0;
+  G.noise_due = 0;
   G.leaf_hpos = -1;
   G.sims_done = root.outcome == IFX_ONGOING ? 0 : P.num_sims;   // a finished game is never searched
   if (root.outcome == IFX_ONGOING) tree_root_noise(P, g, G, root_slot, G.root_nv);   // (no-op unless dirichlet_eps > 0)

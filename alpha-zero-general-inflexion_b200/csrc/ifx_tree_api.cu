@@ -113,6 +113,14 @@ IFX_D void body_root_stats(const TreeParams& P, int g, int32_t* counts, float* q
   if (ns && IFX_LANE0) ns[g] = slot >= 0 ? P.node_head[(int64_t)g * P.C + slot].ns : 0;
 }
 
+// optional Dirichlet root noise for roots expanded by the last wave (see tree_root_noise; ifx_mcts_config)
+IFX_D void body_root_noise(const TreeParams& P, int g) {
+  IfxGame G = P.games[g];
+  if (!G.noise_due) return;
+  tree_root_noise(P, g, G, G.root_slot, G.root_nv);
+  if (IFX_LANE0) P.games[g].noise_due = 0;
+}
+
 IFX_D void body_status(const TreeParams& P, int g, int32_t* status) {
   if (!IFX_LANE0) return;
   const IfxGame G = P.games[g];
@@ -148,6 +156,11 @@ tree_wave_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_strid
   if (g < P.G) tree_wave_game<DBG>(P, g, nn_pi, pi_stride, nn_v, nn_in, buf[w], &mirror[w]);
 }
 
+__global__ void __launch_bounds__(TREE_BLOCK)
+tree_noise_kernel(TreeParams P) {
+  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < P.G) body_root_noise(P, g);
+}
 __global__ void __launch_bounds__(TREE_BLOCK)
 tree_reset_kernel(TreeParams P, const ifx_state* __restrict__ roots, const int32_t* __restrict__ which) {
   const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
@@ -338,6 +351,7 @@ int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const floa
   float buf[IFX_ROW];
   static RootMirror mirror;
   for (int g = 0; g < m->P.G; ++g) tree_wave_game<false>(m->P, g, nn_pi, pi_stride, nn_v, nn_in, buf, &mirror);
+  if (m->P.dir_eps > 0.0f) for (int g = 0; g < m->P.G; ++g) body_root_noise(m->P, g);
   return ifx_after_launch();
 #else
   const bool timed = m->timing && m->n_timed < IFX_TIMING_RING;
@@ -353,6 +367,10 @@ int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const floa
   else
     tree_wave_kernel<false><<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
   if (timed) { cudaEventRecord(m->ev[m->n_timed][1], (cudaStream_t)stream); m->n_timed += 1; }
+  if (m->P.dir_eps > 0.0f) {               // noise mode only: one more (tiny) launch per wave
+    tree_noise_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P);
+    ifx_count_launches(1);
+  }
   return ifx_after_launch();
 #endif
 }

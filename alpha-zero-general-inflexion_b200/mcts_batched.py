@@ -73,6 +73,7 @@ class BatchedMCTS:
             self.nn_pi = self.be.zeros((g, 343), torch.float32)
         self.nn_v = self.be.zeros((g,), torch.float32)
         self.fused_head = bool(fused_head)
+        self.dirichlet_eps = float(dirichlet_eps)
         self.nn_head = self.be.zeros((g, 344), torch.float16) if fused_head else None
         self.waves_run = 0
         self.evals_run = 0
@@ -102,6 +103,11 @@ class BatchedMCTS:
         self.be.check(self.be.dll.ifx_mcts_set_roots(self._h, r.data_ptr(), self.be.stream()))
         self._keep = (r, None)
 
+    @property
+    def waves_per_search(self) -> int:
+        """ifx_mcts_wave calls that complete a move: num_sims + 1 (+1 with root noise: a freshly expanded root yields)."""
+        return self.num_sims + 1 + (1 if self.dirichlet_eps > 0 else 0)
+
     def set_params(self, num_sims: int, cpuct) -> None:
         self.num_sims = int(num_sims)
         self.be.check(self.be.dll.ifx_mcts_set_params(self._h, self.num_sims, float(np.float32(cpuct))))
@@ -130,7 +136,7 @@ class BatchedMCTS:
 
     def search(self, evaluate) -> None:
         """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync."""
-        for _ in range(self.num_sims):
+        for _ in range(self.waves_per_search - 1):
             self.wave()
             self.feed(evaluate)
         self.wave()

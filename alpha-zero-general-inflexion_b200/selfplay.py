@@ -85,7 +85,7 @@ class SelfPlayEngine:
         torch.cuda.synchronize(self.be.device)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            for _ in range(self.num_sims):
+            for _ in range(self.mcts.waves_per_search - 1):
                 self._wave_and_net()
             self.mcts.wave()
 
@@ -100,15 +100,15 @@ class SelfPlayEngine:
                 self._capture()
             self._graph.replay()
         elif wave_timer is None:
-            for _ in range(self.num_sims):
+            for _ in range(self.mcts.waves_per_search - 1):
                 self._wave_and_net()
             self.mcts.wave()
         else:
-            for _ in range(self.num_sims):
+            for _ in range(self.mcts.waves_per_search - 1):
                 wave_timer(self.mcts.wave)
                 self._net_only()
             wave_timer(self.mcts.wave)
-        self.my_launches += self.num_sims + 1 + self.extra_launches_per_search
+        self.my_launches += self.mcts.waves_per_search + self.extra_launches_per_search
 
     def _net_only(self) -> None:
         """Net forward as plain stream launches (timed mode): the stream stays continuously fed, so the event pair

@@ -139,7 +139,9 @@ typedef struct ifx_mcts_config {
                                not depend on T; num_sims+1 waves still complete a move (see ifx_mcts_wave)            */
   float dirichlet_alpha;    /* optional root noise, NOT part of the reference (its MCTS has none): when            */
   float dirichlet_eps;      /* dirichlet_eps > 0, P(root,.) <- (1-eps) P + eps Dir(alpha) over the valid actions,
-                               once per move, drawn on the device from Philox.  0 (default) = reference behaviour   */
+                               once per move, drawn on the device from Philox.  0 (default) = reference behaviour.
+                               A root expanded by a wave yields until the next wave (its priors are perturbed in
+                               between), so a move then needs num_sims+2 calls of ifx_mcts_wave                     */
 } ifx_mcts_config;
 
 typedef struct ifx_mcts ifx_mcts;
