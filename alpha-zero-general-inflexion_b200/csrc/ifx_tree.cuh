@@ -876,8 +876,8 @@ IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
 // ---- root statistics / action choice -----------------------------------------------------------
 IFX_D int tree_root_slot(const TreeParams& P, int g) { return P.games[g].root_slot; }
 
-// Action of Coach.py:66-81: temp = int(move+1 < temp_threshold); buf holds >= 352 ints of scratch.
-IFX_D int tree_sample_action(const TreeParams& P, int g, int temp_threshold, int* buf) {
+// Action of Coach.py:66-81: temp = int(move+1 < temp_threshold); buf / dbuf hold >= 352 ints / doubles of scratch.
+IFX_D int tree_sample_action(const TreeParams& P, int g, int temp_threshold, int* buf, double* dbuf) {
   const IfxGame G = P.games[g];
   const ifx_state root = P.roots[g];
   if (root.outcome != IFX_ONGOING || G.faults) return -1;
@@ -924,14 +924,23 @@ IFX_D int tree_sample_action(const TreeParams& P, int g, int temp_threshold, int
   // Coach.py:81 np.random.choice(343, p=counts/sum): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right')
   const IfxRand4 r = ifx_philox(P.seed, G.game_id, (uint32_t)G.move_idx, 0u, IFX_RNG_ACTION);
   const double u = ifx_uniform53(r);
+  // The float64 divisions are spread over the lanes (11 each, not 686 on every lane: the FP64 pipe is narrow);
+  // only the running sum is sequential, as numpy's cumsum is.
   const double dtot = (double)total;
-  double last = 0.0;
-  for (int a = 0; a < IFX_ACTIONS; ++a) last = ifx_dadd(last, ifx_ddiv((double)buf[a], dtot));
-  double run = 0.0;
-  int idx = 0;
-  for (int a = 0; a < IFX_ACTIONS; ++a) {
-    run = ifx_dadd(run, ifx_ddiv((double)buf[a], dtot));
-    if (ifx_ddiv(run, last) <= u) idx = a + 1;
+  IFX_FOR_LANES(l) { for (int a = l; a < IFX_ACTIONS; a += 32) dbuf[a] = ifx_ddiv((double)buf[a], dtot); }   // p = counts / sum
+  IFX_SYNCWARP();
+  if (IFX_LANE0) {                                           // cdf = cumsum(p)
+    double run = 0.0;
+    for (int a = 0; a < IFX_ACTIONS; ++a) { run = ifx_dadd(run, dbuf[a]); dbuf[a] = run; }
   }
+  IFX_SYNCWARP();
+  const double last = dbuf[IFX_ACTIONS - 1];
+  LaneVar<int> below;                                        // searchsorted(cdf / cdf[-1], u, 'right') = #{a: cdf[a]/last <= u}
+  IFX_FOR_LANES(l) {
+    int c = 0;
+    for (int a = l; a < IFX_ACTIONS; a += 32) c += (ifx_ddiv(dbuf[a], last) <= u) ? 1 : 0;
+    below[l] = c;
+  }
+  const int idx = lanes_sum_i32(below);
   return idx < IFX_ACTIONS ? idx : IFX_ACTIONS - 1;
 }

@@ -189,9 +189,10 @@ tree_root_stats_kernel(TreeParams P, int32_t* counts, float* q32, double* q64, u
 __global__ void __launch_bounds__(TREE_BLOCK)
 tree_sample_kernel(TreeParams P, int temp_threshold, int32_t* __restrict__ actions) {
   __shared__ int buf[TREE_WARPS][IFX_ROW];
+  __shared__ double dbuf[TREE_WARPS][IFX_ROW];
   const int w = threadIdx.x >> 5, g = blockIdx.x * TREE_WARPS + w;
   if (g >= P.G) return;
-  const int a = tree_sample_action(P, g, temp_threshold, buf[w]);
+  const int a = tree_sample_action(P, g, temp_threshold, buf[w], dbuf[w]);
   if (IFX_LANE0) actions[g] = a;
 }
 __global__ void __launch_bounds__(TREE_BLOCK)
@@ -391,7 +392,8 @@ int ifx_mcts_sample_actions(ifx_mcts* m, int32_t temp_threshold, int32_t* action
   if (!m || !actions) return IFX_E_ARG;
 #ifdef IFX_HOSTSIM
   int buf[IFX_ROW];
-  for (int g = 0; g < m->P.G; ++g) actions[g] = tree_sample_action(m->P, g, temp_threshold, buf);
+  double dbuf[IFX_ROW];
+  for (int g = 0; g < m->P.G; ++g) actions[g] = tree_sample_action(m->P, g, temp_threshold, buf, dbuf);
   return ifx_after_launch();
 #else
   tree_sample_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, temp_threshold, actions);

@@ -55,6 +55,11 @@ def _fold(weight, bias, bn):
     return w, b
 
 
+def _capi_check(rc, dll):
+    from ..._capi import check
+    check(rc, dll)
+
+
 def _conv_relu(x, w, b, pad):
     """conv + bias + ReLU in one cuDNN call (fused epilogue) on CUDA; the three-op form elsewhere."""
     if x.is_cuda:
@@ -79,6 +84,16 @@ class FoldedInference:
         w1, b1 = _fold(net.conv1.weight, net.conv1.bias, net.bn1)
         self.w1 = w1.to(self.first_dtype).contiguous(memory_format=torch.channels_last)
         self.b1 = b1.to(self.first_dtype)
+        # conv1 as a GEMM over im2col rows written by libifx_b200 (csrc/ifx_net.cu): [B*49, 64] x [64, 512], taps
+        # c*9 + ky*3 + kx zero-padded from 36 to 64.  CUDA + fp16 only; elsewhere conv1 stays a convolution.
+        self.gemm_conv1 = dev.type == "cuda" and dtype == torch.float16
+        if self.gemm_conv1:
+            w1p = torch.zeros((w1.shape[0], 64), dtype=torch.float32, device=dev)
+            w1p[:, :36] = w1.reshape(w1.shape[0], 36)
+            self.w1p_t = w1p.to(dtype).contiguous().t()               # [64,512] view of the row-major [512,64] weights
+            from ... import _capi
+            self._dll = _capi.lib()
+            self._cols = None
         self.convs = []
         for conv, bn, pad in ((net.conv2, net.bn2, 1), (net.conv3, net.bn3, 0), (net.conv4, net.bn4, 0)):
             w, b = _fold(conv.weight, conv.bias, bn)
@@ -92,6 +107,7 @@ class FoldedInference:
         self.fc1 = (w.to(dtype).contiguous(), b.to(dtype))
         w, b = _fold(net.fc2.weight, net.fc2.bias, net.fc_bn2)
         self.fc2 = (w.to(dtype).contiguous(), b.to(dtype))
+        self.fc1_t, self.fc2_t = self.fc1[0].t(), self.fc2[0].t()
         # both heads in one GEMM: rows 0..342 = fc3, row 343 = fc4
         wh = torch.cat([net.fc3.weight.detach().float(), net.fc4.weight.detach().float()], dim=0)
         bh = torch.cat([net.fc3.bias.detach().float(), net.fc4.bias.detach().float()], dim=0)
@@ -100,12 +116,29 @@ class FoldedInference:
         self.n_act = net.action_size
         self.device = dev
 
+    def _conv1_gemm(self, x: torch.Tensor):
+        """conv1 + BN + ReLU as im2col (our kernel) + one GEMM with a fused bias+ReLU epilogue (cuBLASLt)."""
+        n = x.shape[0]
+        x = x.contiguous()
+        if self._cols is None or self._cols.shape[0] != n * 49:
+            self._cols = torch.empty((n * 49, 64), dtype=self.dtype, device=x.device)
+        _capi_check(self._dll.ifx_net_im2col3x3(x.data_ptr(), n, self._cols.data_ptr(),
+                                                torch.cuda.current_stream(x.device).cuda_stream), self._dll)
+        s = torch._addmm_activation(self.b1, self._cols, self.w1p_t, use_gelu=False)      # [n*49, 512] = NHWC
+        return s.view(n, 7, 7, -1).permute(0, 3, 1, 2)                       # NCHW view of channels-last memory
+
     def _trunk(self, x: torch.Tensor):
-        x = x.to(self.first_dtype).contiguous(memory_format=torch.channels_last)
-        s = _conv_relu(x, self.w1, self.b1, 1).to(self.dtype)
+        if self.gemm_conv1 and x.is_cuda and x.dtype == torch.float32 and tuple(x.shape[1:]) == (4, 7, 7):
+            s = self._conv1_gemm(x)
+        else:
+            x = x.to(self.first_dtype).contiguous(memory_format=torch.channels_last)
+            s = _conv_relu(x, self.w1, self.b1, 1).to(self.dtype)
         for w, b, pad in self.convs:
             s = _conv_relu(s, w, b, pad)
         s = s.permute(0, 2, 3, 1).reshape(s.shape[0], -1)                    # NHWC flatten: a view for channels-last
+        if s.is_cuda and self.dtype != torch.float32:                        # bias + ReLU in the GEMM epilogue
+            s = torch._addmm_activation(self.fc1[1], s, self.fc1_t, use_gelu=False)
+            return torch._addmm_activation(self.fc2[1], s, self.fc2_t, use_gelu=False)
         s = F.relu(F.linear(s, *self.fc1))
         return F.relu(F.linear(s, *self.fc2))
 

@@ -248,7 +248,7 @@ def run_ours(a):
                          auto_restart=True, restart_stride=world * a.games)
     if a.net == "stub":                                    # deterministic stub evaluator, one kernel per wave (csrc/ifx_stub.cu)
         eng.evaluate = stub_kernel_evaluator(eng.mcts)
-        eng.extra_launches_per_search = a.sims
+    eng.extra_launches_per_search = a.sims                 # per net evaluation one kernel of ours: the stub, or conv1's im2col
 
     def barrier():
         torch.cuda.synchronize()

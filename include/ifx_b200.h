@@ -239,6 +239,15 @@ IFX_API int ifx_mcts_counters(ifx_mcts* m, uint64_t* counters, void* stream);
 IFX_API int ifx_stub_policy_value(const float* nn_in, int64_t n, const int64_t* coef, int dyadic, float* pi,
                                   int64_t pi_stride, float* v, void* stream);
 
+/* ---- input stage of the policy/value net ------------------------------------------------------- */
+
+/* im2col of the net input for conv1 (3x3, pad 1; inflexion/pytorch/InflexionNNet.py:24,41 of the reference):
+ * planes float32 [n][4][7][7] -> out binary16 [n*49][64], row = position*49 + y*7 + x, column = c*9 + ky*3 + kx for
+ * the 36 taps (zero outside the board), columns 36..63 zero.  conv1 + BN + ReLU then is ONE tensor-core GEMM
+ * [n*49,64] x [64,512] with a bias+ReLU epilogue, and its output is the channels-last activation conv2 reads
+ * (NNetWrapper.predict_batch / predict_head, the batched form of NNet.py:78-94).  GPU build only. */
+IFX_API int ifx_net_im2col3x3(const float* planes, int64_t n, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

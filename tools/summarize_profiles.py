@@ -51,10 +51,37 @@ def full_summary(rep, dst, title, extra=""):
                 f.write(f"traffic (dram read+write) per launch: {(float(r[i_r]) * sc[units[i_r]] + float(r[i_w]) * sc[units[i_w]]) / 1e6:.1f} MB\n")
     print(open(dst).read())
 
+def traffic_of(rep):
+    """mean dram read+write bytes per profiled launch of a --set full capture"""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.split("\n")))
+    hdr, units = rows[0], rows[1]
+    i_r, i_w, i_t = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    sc = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
+    tot = [float(r[i_r]) * sc[units[i_r]] + float(r[i_w]) * sc[units[i_w]] for r in rows[2:] if len(r) > i_w]
+    dur = [float(r[i_t]) for r in rows[2:] if len(r) > i_t]
+    return {"dram_bytes_per_launch": sum(tot) / len(tot), "launches_profiled": len(tot),
+            "ncu_duration_" + units[i_t]: sum(dur) / len(dur), "source": os.path.basename(rep)}
+
 g = os.path.join(ROOT, "gpurun_out")
 launch_list(os.path.join(g, "launches_default_r1.csv"), os.path.join(OUT, f"{tag}_launches_bench_default.txt"),
             "bench.py --steps 1 --warmup 3 (default net, 4096 games x 100 sims): per-kernel device time")
 full_summary(os.path.join(g, "tree_default_r1.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_tree_wave_kernel.txt"),
              "tree_wave_kernel inside bench.py (default net, 4096 games x 100 sims/move)")
+full_summary(os.path.join(g, "tree_stub_r1.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_tree_wave_kernel_stub.txt"),
+             "tree_wave_kernel inside bench.py --net stub (tree + rules only, 4096 games x 100 sims/move)")
 full_summary(os.path.join(g, "rules_r1.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_rules_mask_step_kernel.txt"),
              "rules_mask_step_kernel, bench.py --workload rules (4 Mi states per launch)")
+traffic = {"tree_wave_kernel": {"default": traffic_of(os.path.join(g, "tree_default_r1.ncu-rep")),
+                                "stub": traffic_of(os.path.join(g, "tree_stub_r1.ncu-rep"))},
+           "rules_mask_step_kernel": {"rules": traffic_of(os.path.join(g, "rules_r1.ncu-rep"))}}
+json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+print(json.dumps(traffic, indent=1))
+for name in ("bench_default", "bench_stub", "bench_rules", "bench_reference"):
+    src = os.path.join(g, name + ".json")
+    if os.path.exists(src):
+        open(os.path.join(OUT, f"{tag}_{name}.json"), "w").write(open(src).read())
+for name in ("trace_default", "trace_stub"):
+    src = os.path.join(g, name + ".log")
+    if os.path.exists(src):
+        open(os.path.join(OUT, f"{tag}_{name}.txt"), "w").write("# tools/trace_wave.py 4096 " + name.split("_")[1] + ": per-warp %globaltimer phases of the wave kernel\n" + open(src).read())
