@@ -288,3 +288,32 @@ def test_optional_dirichlet_root_noise(backend):
     assert 0.75 * var_theory < e.var() < 1.3 * var_theory, (e.var(), var_theory)
     # different games draw different noise
     assert len({e[g].tobytes() for g in range(G)}) == G
+
+
+def test_small_tables_probe_chains_and_slot_reuse(backend):
+    """A tight node pool (64 slots, 128 hash entries: load factor up to 0.5, probe chains longer than one 8-entry
+    group, slots reclaimed and reused every move) must give the same search as the default-sized tables."""
+    G, sims, moves = 4, 20, 6
+    out = []
+    for nodes in (None, 64):
+        m = BatchedMCTS(G, sims, 1.0, seed=31, backend=backend, nodes_per_game=nodes)
+        m.reset(start_states(G, 343))
+        rec = []
+        for _ in range(moves):
+            m.search(stub_eval("float"))
+            m.raise_on_faults()
+            s = m.root_stats(want_q=True)
+            acts = m.sample_actions(3)
+            rec.append((s["counts"].cpu().numpy().copy(), s["q32"].cpu().numpy().copy(), acts.cpu().numpy().copy()))
+            m.advance(acts)
+        out.append(rec)
+    assert m.cfg.nodes_per_game == 64 and m.cfg.hash_per_game == 128
+    for (c0, q0, a0), (c1, q1, a1) in zip(*out):
+        assert np.array_equal(c0, c1) and q0.tobytes() == q1.tobytes() and np.array_equal(a0, a1)
+
+
+def test_zero_sized_calls_are_noops(backend):
+    dll = backend.dll
+    assert dll.ifx_stub_policy_value(None, 0, None, 0, None, 343, None, None) == 0
+    assert dll.ifx_stub_policy_value(None, 1, None, 0, None, 343, None, None) == -1      # IFX_E_ARG
+    assert dll.ifx_net_im2col3x3(None, 0, None, None) == 0

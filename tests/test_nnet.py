@@ -153,3 +153,17 @@ def test_head_into_equals_call_on_gpu():
     pi2 = torch.exp(torch.log_softmax(out[:, :343].float(), dim=1))
     v2 = torch.tanh(out[:, 343].float())
     assert torch.allclose(pi, pi2, atol=1e-6) and torch.allclose(v, v2, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_im2col_kernel_matches_unfold_on_gpu():
+    """ifx_net_im2col3x3 (conv1's input stage) == torch's unfold of the same planes, bit for bit, zero-padded to 64."""
+    from inflexion_b200 import _capi
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(random_planes(300, seed=9)).to(dev)
+    out = torch.full((300 * 49, 64), 7.0, dtype=torch.float16, device=dev)
+    dll = _capi.lib()
+    _capi.check(dll.ifx_net_im2col3x3(x.data_ptr(), 300, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), dll)
+    ref = torch.nn.functional.unfold(x, kernel_size=3, padding=1)            # [300, 36, 49], rows c*9 + ky*3 + kx
+    ref = ref.permute(0, 2, 1).reshape(300 * 49, 36).to(torch.float16)
+    assert torch.equal(out[:, :36], ref) and float(out[:, 36:].abs().max()) == 0.0
