@@ -77,7 +77,24 @@ traffic = {"tree_wave_kernel": {"default": traffic_of(os.path.join(g, "tree_defa
            "rules_mask_step_kernel": {"rules": traffic_of(os.path.join(g, "rules_r1.ncu-rep"))}}
 json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
-for name in ("bench_default", "bench_stub", "bench_rules", "bench_reference"):
+rep = os.path.join(g, "net_convs_r1.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.split("\n")))
+    hdr, units = rows[0], rows[1]
+    want = ["Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_tensor.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum",
+            "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
+            "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+    with open(os.path.join(OUT, f"{tag}_ncu_net_convolutions.txt"), "w") as f:
+        f.write("# the policy/value net's 512-channel convolutions inside bench.py (cuDNN/CUTLASS library kernels, fp16 in / fp32 accumulate)\n"
+                "# source: ncu --set full --clock-control none (net_convs_r1.ncu-rep), one column per profiled launch\n")
+        for w in want:
+            if w in hdr:
+                i = hdr.index(w)
+                f.write(f"{w} [{units[i]}]: {' | '.join(r[i][:60] for r in rows[2:] if len(r) > i)}\n")
+    print(open(os.path.join(OUT, f"{tag}_ncu_net_convolutions.txt")).read())
+for name in ("bench_default", "bench_stub", "bench_rules", "bench_reference", "bench_sims200"):
     src = os.path.join(g, name + ".json")
     if os.path.exists(src):
         open(os.path.join(OUT, f"{tag}_{name}.json"), "w").write(open(src).read())
