@@ -44,12 +44,15 @@ def test_4096_games_x_100_sims_properties_and_oracle_sample(cuda_backend):
         assert bool((counts[~valid] == 0).all())                              # visits only on valid actions
         # conservation: every simulation that passes the root increments exactly one root edge and Ns (MCTS.py:136-144)
         assert torch.equal(counts.sum(dim=1), ns)
+        live = roots[:, 45] == 0                      # a game can already be over at ply 3 (its only stack captured)
+        assert bool(live.all()) if mv < 3 else bool(live.any())
         # the first search of an episode expands the root with its first simulation; later roots are reused subtrees
-        assert bool((ns >= SIMS - 1).all()) if mv == 0 else bool((ns >= SIMS).all())
-        assert bool((ns == SIMS - 1).all()) if mv == 0 else True
-        a = acts.long()
-        assert bool((a >= 0).all()) and bool(valid[torch.arange(G, device=be.device), a].all())
-        assert bool((counts[torch.arange(G, device=be.device), a] > 0).all())   # sampled from the visit distribution
+        assert bool((ns[live] == SIMS - 1).all()) if mv == 0 else bool((ns[live] >= SIMS).all())
+        assert bool((ns[~live] == 0).all()) and bool((acts[~live] == -1).all())     # finished games are never searched
+        a = acts.long().clamp_min(0)
+        idx = torch.arange(G, device=be.device)
+        assert bool((acts[live] >= 0).all()) and bool(valid[idx, a][live].all())
+        assert bool((counts[idx, a][live] > 0).all())                         # sampled from the visit distribution
         if mv < 2:                                                            # determinism in the seed
             assert torch.equal(counts, again[mv][1]) and torch.equal(acts, again[mv][3])
         # a game does not depend on the batch it is played in (what sharding over ranks relies on)
