@@ -132,10 +132,14 @@ struct TreeParams {
   uint64_t seed;
 };
 
+// 108-bit node key -> table index bits: four 32-bit multiplies and a 32-bit finaliser (the table is indexed by the
+// low bits; 64-bit multiplies cost 3-4 instructions each on this datapath)
 IFX_HD uint32_t ifx_hash_key(uint64_t k0, uint64_t k1) {
-  uint64_t h = k0 * 0x9E3779B97F4A7C15ull ^ (k1 + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
-  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-  return (uint32_t)h;
+  const uint32_t a = (uint32_t)k0, b = (uint32_t)(k0 >> 32), c = (uint32_t)k1, d = (uint32_t)(k1 >> 32);
+  uint32_t h = (a * 0x9E3779B1u) ^ ((b + 0x7F4A7C15u) * 0x85EBCA77u) ^ ((c ^ 0x27D4EB2Fu) * 0xC2B2AE3Du) ^
+               ((d + 0x165667B1u) * 0x27D4EB2Fu);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
 }
 
 // Every pool is [G][...]: a warp works on ONE game, so the wave kernel rebases the pointers to its game once and
@@ -209,10 +213,10 @@ IFX_D int tree_hash_resolve(const TreeParams& P, int g, uint64_t k0, uint64_t k1
 // ---- the root's rows, mirrored in shared memory for the length of a wave ----
 // Every simulation starts at the root, and the root slot is known as soon as the game record has arrived, i.e.
 // long before the pending leaf has been expanded and backed up.  Its three rows, header and key are therefore
-// copied into shared memory with cp.async right away (no registers held, the copy flies under the expansion),
+// copied into shared memory by the TMA engine right away (no registers held, the copy flies under the expansion),
 // the backup patches the one edge it changes, and every simulation of the wave selects from the mirror: one
 // HBM read of the root per wave and no dependent round trip at the start of a simulation.
-struct alignas(16) RootMirror { float rows[3 * IFX_ROW]; IfxHead head; IfxKey key; };
+struct alignas(16) RootMirror { float rows[3 * IFX_ROW]; IfxHead head; IfxKey key; uint64_t mbar; uint64_t pad; };
 
 #ifdef IFX_HOSTSIM
 static inline void ifx_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
@@ -222,14 +226,59 @@ IFX_D void ifx_cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 IFX_D void ifx_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP in SASS)
+IFX_D void ifx_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+                  "r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
+}
 #endif
 
+// Top of the wave: the common fetch, issued by ONE lane as five TMA bulk copies (three rows of ceil(nv/4) 16-byte
+// chunks, header, key) that complete on the warp's mbarrier -- six instructions instead of a cp.async loop over all
+// lanes.  The source was written by earlier launches, so no proxy fence is needed.
 IFX_D void tree_mirror_fetch(const TreeParams& P, int g, int slot, int nv, RootMirror* M) {
-  const int chunks = (nv + 3) >> 2;                         // 16-byte chunks per row that hold entries (<= 88)
+  const uint32_t bytes = (uint32_t)((nv + 3) >> 2) * 16u;
+  const char* src = reinterpret_cast<const char*>(tree_row(P, g, slot, 0));
+#ifdef IFX_HOSTSIM
+  for (int which = 0; which < 3; ++which) memcpy(M->rows + which * IFX_ROW, src + which * 4 * IFX_ROW, bytes);
+  M->head = P.node_head[(int64_t)g * P.C + slot];
+  M->key = P.node_key[(int64_t)g * P.C + slot];
+#else
+  if (IFX_LANE0) {
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&M->mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(3u * bytes + 32u) : "memory");
+    if (bytes) {
+      ifx_bulk_g2s(M->rows, src, bytes, &M->mbar);
+      ifx_bulk_g2s(M->rows + IFX_ROW, src + 4 * IFX_ROW, bytes, &M->mbar);
+      ifx_bulk_g2s(M->rows + 2 * IFX_ROW, src + 8 * IFX_ROW, bytes, &M->mbar);
+    }
+    ifx_bulk_g2s(&M->head, &P.node_head[(int64_t)g * P.C + slot], 16u, &M->mbar);
+    ifx_bulk_g2s(&M->key, &P.node_key[(int64_t)g * P.C + slot], 16u, &M->mbar);
+  }
+#endif
+}
+IFX_D void tree_mirror_wait(RootMirror* M) {
+#ifndef IFX_HOSTSIM
+  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&M->mbar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(mb) : "memory");
+  }
+#endif
+  IFX_SYNCWARP();
+}
+// A root expanded in this very wave (once per move at most): its rows were just written with ordinary stores, so
+// they are fetched with cp.async (the same proxy) and waited for at once.
+IFX_D void tree_mirror_fetch_now(const TreeParams& P, int g, int slot, int nv, RootMirror* M) {
+  const int chunks = (nv + 3) >> 2;
   const char* src = reinterpret_cast<const char*>(tree_row(P, g, slot, 0));
   char* dst = reinterpret_cast<char*>(M->rows);
   IFX_FOR_LANES(l) {
-    for (int i = l; i < chunks; i += 32) {                  // one pass for nv <= 128
+    for (int i = l; i < chunks; i += 32) {
       ifx_cp_async16(dst + 16 * i, src + 16 * i);
       ifx_cp_async16(dst + 16 * i + 4 * IFX_ROW, src + 16 * i + 4 * IFX_ROW);
       ifx_cp_async16(dst + 16 * i + 8 * IFX_ROW, src + 16 * i + 8 * IFX_ROW);
@@ -237,8 +286,9 @@ IFX_D void tree_mirror_fetch(const TreeParams& P, int g, int slot, int nv, RootM
     if (l == 0) ifx_cp_async16(&M->head, &P.node_head[(int64_t)g * P.C + slot]);
     if (l == 1) ifx_cp_async16(&M->key, &P.node_key[(int64_t)g * P.C + slot]);
   }
+  ifx_cp_async_wait();
+  IFX_SYNCWARP();
 }
-IFX_D void tree_mirror_wait() { ifx_cp_async_wait(); IFX_SYNCWARP(); }
 
 // ---- one edge of the backup (MCTS.py:136-142 under NEP-50 promotion) ----
 // (raw N, Q32) were loaded ahead of time; q64 is touched only for Python-float edges.  `child` (>= 0) refreshes
@@ -679,13 +729,13 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
   if (G.pending && G.path_len > 8) {
     IFX_FOR_LANES(l) { if (l >= 8) path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
   }
-  if (G.faults) { if (mirror_slot >= 0) tree_mirror_wait(); return; }
+  if (G.faults) { if (mirror_slot >= 0) tree_mirror_wait(mirror); return; }
   if (DBG) dbg_t1 = ifx_now_ns() + (uint64_t)(G.pending & 0) + (uint64_t)(leaf.turn & 0);
   if (G.pending) {
     int leaf_nv = 0;
     const int slot = tree_expand(P, g, G, leaf, pol, buf, P.logits == 2, &leaf_nv);
     if (DBG) dbg_t2 = ifx_now_ns();
-    if (mirror_slot >= 0) tree_mirror_wait();               // the backup patches the mirror: it must have landed
+    if (mirror_slot >= 0) tree_mirror_wait(mirror);         // the backup patches the mirror: it must have landed
     if (slot >= 0) {
       if (G.path_len == 0) {                                // the root itself was the leaf
         G.root_slot = slot; G.root_nv = leaf_nv;
@@ -700,7 +750,7 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     G.pending = 0;
     if (DBG) dbg_t3 = ifx_now_ns();
   } else if (mirror_slot >= 0) {
-    tree_mirror_wait();
+    tree_mirror_wait(mirror);
   }
   int term_left = P.term_budget > 0 ? P.term_budget : 0x7fffffff;
   while (!G.faults && G.sims_done < P.num_sims && term_left > 0 && !G.noise_due) {
@@ -712,8 +762,7 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     bool inflight = slot >= 0;
     if (inflight) {
       if (mirror_slot != slot) {                            // the root was expanded in this very wave (once per move at most)
-        tree_mirror_fetch(P, g, slot, G.root_nv, mirror);
-        tree_mirror_wait();
+        tree_mirror_fetch_now(P, g, slot, G.root_nv, mirror);
         mirror_slot = slot;
       }
       tree_rows_from_mirror(mirror, rows);

@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--workload", default="selfplay", choices=["selfplay", "rules"],
                     help="selfplay = the headline (BASELINE configs[2]); rules = the rules kernel alone (configs[1] shape)")
     ap.add_argument("--states", type=int, default=4 * 1024 * 1024, help="states per launch for --workload rules")
+    ap.add_argument("--nodes", type=int, default=None, help="node pool slots per game (default: mcts_batched.default_pool_size)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -244,7 +245,7 @@ def run_ours(a):
         evaluate, fused = None, False                      # installed below: the stub is a kernel of the library
 
     eng = SelfPlayEngine(a.games, a.sims, evaluate, cpuct=1.0, temp_threshold=30, seed=2023, max_turns=343,
-                         game_id_base=rank * a.games, record=True, backend=be, fused_head=fused,
+                         game_id_base=rank * a.games, record=True, backend=be, fused_head=fused, nodes_per_game=a.nodes,
                          auto_restart=True, restart_stride=world * a.games)
     if a.net == "stub":                                    # deterministic stub evaluator, one kernel per wave (csrc/ifx_stub.cu)
         eng.evaluate = stub_kernel_evaluator(eng.mcts)
