@@ -50,13 +50,25 @@ class NNetWrapper(NeuralNet):
         pis_all = torch.as_tensor(np.array([e[1] for e in examples], dtype=np.float32))
         vs_all = torch.as_tensor(np.array([e[2] for e in examples], dtype=np.float32))
         params = [p for p in self.nnet.parameters() if p.requires_grad]
+        # steps per epoch: one pass over the examples (NNet.py:50).  Under torch.distributed the examples are
+        # rank-local and their number differs from rank to rank (games end at different moves), so every rank must
+        # agree on the count or the gradient all-reduce deadlocks: one pass over the GLOBAL set at a global batch of
+        # world x batch_size.
+        n_total = len(examples)
+        if dist and world > 1:
+            t = torch.tensor([n_total], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t)
+            n_total = int(t[0])
+            if len(examples) == 0:
+                raise ValueError("NNetWrapper.train: this rank has no examples")
+        steps = int(n_total / (args.batch_size * world))
         history = []
         for epoch in range(args.epochs):
             if verbose:
                 print("EPOCH ::: " + str(epoch + 1))
             self.nnet.train()
             pi_losses, v_losses = AverageMeter(), AverageMeter()
-            for _ in range(int(len(examples) / args.batch_size)):
+            for _ in range(steps):
                 ids = torch.from_numpy(np.random.randint(len(examples), size=args.batch_size))
                 boards = boards_all[ids].to(self.device, non_blocking=True)
                 target_pis = pis_all[ids].to(self.device, non_blocking=True)

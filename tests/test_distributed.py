@@ -69,9 +69,10 @@ def _train_worker(rank, world, port, out_dir):
     torch.manual_seed(0)                                     # same initial weights on every rank
     w = nnet_mod.NNetWrapper(Shape(), device="cpu", infer_dtype=torch.float32)
     np.random.seed(100 + rank)                               # different batches per rank
-    planes = random_planes(48, seed=rank).astype(np.int64)
-    pis = np.full((48, 343), 1.0 / 343)
-    examples = [(planes[i], pis[i].tolist(), float((-1) ** (i + rank))) for i in range(48)]
+    n = 48 + 40 * rank                                       # rank-local example counts differ (games end at different
+    planes = random_planes(n, seed=rank).astype(np.int64)    # moves): the ranks must still agree on the number of steps
+    pis = np.full((n, 343), 1.0 / 343)
+    examples = [(planes[i], pis[i].tolist(), float((-1) ** (i + rank))) for i in range(n)]
     w.train(examples, verbose=False)
     flat = torch.cat([p.detach().reshape(-1) for p in w.nnet.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
