@@ -131,3 +131,50 @@ def test_sharded_arena_and_example_gather(tmp_path):
         eng.play_move()
     planes, pi, v = eng.examples()
     assert len(v) > 0 and np.array_equal(got["planes"], planes) and np.array_equal(got["pi"], pi) and np.array_equal(got["v"], v)
+
+
+def _learn_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import inflexion_b200  # noqa: F401
+    import inflexion_b200.backend as backend_mod
+    from hostsim import hostsim_backend
+    from inflexion_b200.Coach import Coach
+    from inflexion_b200.inflexion.InflexionGame import InflexionGame
+    from inflexion_b200.inflexion.pytorch import NNet as nnet_mod
+    from inflexion_b200.utils import dotdict
+    backend_mod._DEFAULT = hostsim_backend()                 # test seam: the kernels' logic-check build on the CPU
+    nnet_mod.args.update(cuda=False, epochs=1, batch_size=32, num_channels=8)
+    torch.manual_seed(0)                                     # same initial weights on every rank
+    np.random.seed(3)
+    game = InflexionGame(7, max_turns=6, max_power=6)
+    nnet = nnet_mod.NNetWrapper(game, device="cpu", infer_dtype=torch.float32)
+    args = dotdict({"numIters": 1, "numEps": 4, "tempThreshold": 3, "numMCTSSims": 6, "cpuct": 1, "maxlenOfQueue": 200000,
+                    "numItersForTrainExamplesHistory": 2, "checkpoint": os.path.join(out_dir, "ckpt"), "arenaCompare": 4})
+    coach = Coach(game, nnet, args)
+    coach.learn()                                            # self-play (2 games per rank) -> train (all-reduce) -> checkpoint
+    n_local = sum(len(d) for d in coach.trainExamplesHistory)
+    flat = torch.cat([p.detach().reshape(-1) for p in nnet.nnet.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_local]))
+    if rank == 0:
+        torch.save({"weights": gathered, "counts": [int(c) for c in counts]}, os.path.join(out_dir, "learn.pt"))
+    dist.destroy_process_group()
+
+
+def test_coach_learn_iteration_under_torch_distributed(tmp_path):
+    """Coach.learn with an initialised process group: games shard by rank, example counts differ per rank, training
+    stays in lock-step (same weights everywhere), rank 0 writes the checkpoint, every rank its own example shard."""
+    port = _free_port()
+    mp.spawn(_learn_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(os.path.join(tmp_path, "learn.pt"))
+    assert torch.equal(got["weights"][0], got["weights"][1])
+    assert all(c > 0 and c % 36 == 0 for c in got["counts"])
+    ck = os.path.join(tmp_path, "ckpt")
+    assert os.path.isfile(os.path.join(ck, "temp.pth.tar"))
+    assert os.path.isfile(os.path.join(ck, "checkpoint_0.pth.tar.examples.rank0"))
+    assert os.path.isfile(os.path.join(ck, "checkpoint_0.pth.tar.examples.rank1"))
