@@ -67,6 +67,24 @@ class Coach:
             return dist.get_rank(), dist.get_world_size()
         return 0, 1
 
+    def _job_seed(self) -> int:
+        """A fresh seed from numpy's global stream, the same on every rank of a torch.distributed job (rank 0's)."""
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+        rank, world = self._dist()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([seed], dtype=torch.int64, device=getattr(self.nnet, "device", "cpu"))
+            dist.broadcast(t, 0)
+            seed = int(t[0])
+        return seed
+
+    def _evaluator(self):
+        """(evaluate, fused_head): on a GPU the net hands its raw binary16 head output to the tree kernel (softmax and
+        tanh fused there); elsewhere the ordinary batched forward."""
+        fused = hasattr(self.nnet, "predict_head") and getattr(getattr(self.nnet, "device", None), "type", "cpu") == "cuda"
+        return (self.nnet.predict_head if fused else self.nnet.predict_batch), fused
+
     def selfPlayBatch(self, num_games: int, seed: int = 0, game_id_base: int = 0, gather: bool = False):
         """``num_games`` episodes at once on the device -> list of (planes, pi list, v) in the reference's order.
 
@@ -80,9 +98,7 @@ class Coach:
         per = -(-int(num_games) // world)
         if world > 1 and per * world != num_games:
             raise ValueError(f"numEps={num_games} must be a multiple of the world size {world}")
-        # on a GPU the net hands its raw binary16 head output to the tree kernel (softmax/tanh fused there)
-        fused = hasattr(self.nnet, "predict_head") and getattr(getattr(self.nnet, "device", None), "type", "cpu") == "cuda"
-        evaluate = self.nnet.predict_head if fused else self.nnet.predict_batch
+        evaluate, fused = self._evaluator()
         eng = SelfPlayEngine(per, int(self.args.numMCTSSims), evaluate, cpuct=self.args.cpuct,
                              temp_threshold=int(self.args.tempThreshold), seed=seed, max_turns=self.game._max_turns,
                              game_id_base=game_id_base + rank * per, fused_head=fused)
@@ -96,20 +112,13 @@ class Coach:
         return [(planes[i], pi[i].tolist(), float(v[i])) for i in range(len(v))]
 
     def learn(self):
-        pit_interval = 5
+        pit_interval = int(dict(self.args).get("pitInterval", 5))       # the reference hard-codes 5 (Coach.py:101,155)
         for i in range(1, self.args.numIters + 1):
             log.info(f"Starting Iter #{i} ...")
             rank, world = self._dist()
             if not self.skipFirstSelfPlay or i > 1:
                 examples = deque([], maxlen=self.args.maxlenOfQueue)
-                seed = int(np.random.randint(0, 2 ** 31 - 1))
-                if world > 1:                            # one seed for the whole job (rank 0's)
-                    import torch
-                    import torch.distributed as dist
-                    t = torch.tensor([seed], dtype=torch.int64, device=getattr(self.nnet, "device", "cpu"))
-                    dist.broadcast(t, 0)
-                    seed = int(t[0])
-                examples += self.selfPlayBatch(int(self.args.numEps), seed=seed,
+                examples += self.selfPlayBatch(int(self.args.numEps), seed=self._job_seed(),
                                                gather=bool(dict(self.args).get("gatherExamples", False)))
                 self.trainExamplesHistory.append(examples)
             if len(self.trainExamplesHistory) > self.args.numItersForTrainExamplesHistory:
@@ -129,10 +138,12 @@ class Coach:
             log.info("PITTING AGAINST BASELINES")
             if hasattr(self.nnet, "predict_batch"):
                 # all arenaCompare games of a pairing at once on the device (same players, same colour split)
+                # (sharded over the ranks of a torch.distributed job; only the W/L/D counters are all-reduced)
                 from .arena_batched import BatchedArena
+                evaluate, fused = self._evaluator()
                 for name in ("random", "greedy"):
-                    arena = BatchedArena(self.nnet.predict_batch, int(self.args.numMCTSSims), self.args.cpuct, opponent=name,
-                                         seed=int(np.random.randint(0, 2 ** 31 - 1)), max_turns=self.game._max_turns)
+                    arena = BatchedArena(evaluate, int(self.args.numMCTSSims), self.args.cpuct, opponent=name,
+                                         seed=self._job_seed(), max_turns=self.game._max_turns, fused_head=fused)
                     p1wins, p2wins, draws = arena.playGames(int(self.args.arenaCompare))
                     log.info(f"NEW/{name.capitalize()}Player WINS : {p1wins} / {p2wins} ; DRAWS : {draws}")
                 continue
@@ -157,6 +168,9 @@ class Coach:
     def loadTrainExamples(self):
         model_file = os.path.join(self.args.load_folder_file[0], self.args.load_folder_file[1])
         examples_file = model_file + ".examples"
+        rank, world = self._dist()
+        if world > 1 and os.path.isfile(examples_file + f".rank{rank}"):      # this rank's shard of a distributed run
+            examples_file += f".rank{rank}"
         if not os.path.isfile(examples_file):
             log.warning(f'File "{examples_file}" with trainExamples not found!')
             if input("Continue? [y|n]") != "y":

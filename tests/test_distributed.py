@@ -152,7 +152,8 @@ def _learn_worker(rank, world, port, out_dir):
     game = InflexionGame(7, max_turns=6, max_power=6)
     nnet = nnet_mod.NNetWrapper(game, device="cpu", infer_dtype=torch.float32)
     args = dotdict({"numIters": 1, "numEps": 4, "tempThreshold": 3, "numMCTSSims": 6, "cpuct": 1, "maxlenOfQueue": 200000,
-                    "numItersForTrainExamplesHistory": 2, "checkpoint": os.path.join(out_dir, "ckpt"), "arenaCompare": 4})
+                    "numItersForTrainExamplesHistory": 2, "checkpoint": os.path.join(out_dir, "ckpt"), "arenaCompare": 4,
+                    "pitInterval": 1})                        # pit (sharded Arena vs Random and Greedy) in this iteration too
     coach = Coach(game, nnet, args)
     coach.learn()                                            # self-play (2 games per rank) -> train (all-reduce) -> checkpoint
     n_local = sum(len(d) for d in coach.trainExamplesHistory)
