@@ -13,17 +13,20 @@ from .InflexionGame import InflexionGame, Move  # noqa: F401  (re-exported like 
 
 
 class Player:
+    """Protocol of the reference (InflexionPlayers.py:10-21): ``play(game) -> action``, ``reset() -> fresh player``,
+    hashable by a per-object id (Arena keys its score table by player)."""
+
     def __init__(self):
         self.id = uuid.uuid4()
 
-    def play(self, game: Game) -> int:
-        raise NotImplementedError
-
-    def reset(self):
-        raise NotImplementedError
-
     def __hash__(self):
         return hash(self.id)
+
+    def play(self, game: Game) -> int:
+        raise NotImplementedError(f"{type(self).__name__}.play")
+
+    def reset(self) -> "Player":
+        return type(self)()                                  # stateless players: a new object of the same kind
 
 
 class RandomPlayer(Player):
@@ -32,9 +35,6 @@ class RandomPlayer(Player):
     def play(self, game: Game) -> int:
         valid = np.flatnonzero(game.valid_actions_mask() == 1)
         return int(np.random.choice(valid))
-
-    def reset(self):
-        return RandomPlayer()
 
 
 class GreedyPlayer(Player):
@@ -51,9 +51,6 @@ class GreedyPlayer(Player):
         best = scores.max()
         return int(valid[np.flatnonzero(scores == best)[-1]])
 
-    def reset(self):
-        return GreedyPlayer()
-
 
 class HumanPlayer(Player):
     """Reads "r q m" from stdin (InflexionPlayers.py:37-58)."""
@@ -67,9 +64,6 @@ class HumanPlayer(Player):
             a = game.move_to_action((Move.from_num(m), r, q))
             if valid[a]:
                 return a
-
-    def reset(self):
-        return HumanPlayer()
 
 
 class MCTSPlayer(Player):

@@ -2,33 +2,39 @@
 
 
 class AverageMeter:
-    """Running mean of a scalar (used for the loss read-outs of NNetWrapper.train)."""
+    """Weighted running mean of a scalar; prints as the mean in ``%.2e`` (the loss read-outs of NNetWrapper.train).
+    Attributes as in the reference: ``val`` (last value), ``sum``, ``count``, ``avg``."""
+
+    __slots__ = ("val", "sum", "count")
 
     def __init__(self):
-        self.val = self.avg = self.sum = 0.0
-        self.count = 0
+        self.val, self.sum, self.count = 0.0, 0.0, 0
 
-    def update(self, val, n=1):
+    @property
+    def avg(self) -> float:
+        return self.sum / self.count if self.count else 0.0
+
+    def update(self, val, n: int = 1) -> None:
         self.val = val
-        self.sum += val * n
+        self.sum += n * val
         self.count += n
-        self.avg = self.sum / self.count
 
-    def __repr__(self):
-        return f"{self.avg:.2e}"
+    def __repr__(self) -> str:
+        return format(self.avg, ".2e")
 
 
 class dotdict(dict):
-    """dict with attribute access; pickles as a list of pairs like the reference's (utils.py:23-40)."""
+    """dict with attribute access (``args.numMCTSSims``); pickles as a list of (key, value) pairs like the
+    reference's, so argument objects saved by either implementation load in the other (utils.py:23-40)."""
 
     def __getattr__(self, name):
         try:
             return self[name]
         except KeyError:
-            raise AttributeError(name) from None
+            raise AttributeError(name) from None          # lets hasattr()/getattr(default) behave
 
     def __getstate__(self):
         return list(self.items())
 
-    def __setstate__(self, state):
-        self.update(dict(state))
+    def __setstate__(self, pairs):
+        self.update(pairs)
