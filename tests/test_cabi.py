@@ -51,3 +51,14 @@ def test_product_has_no_cpu_fallback(monkeypatch):
     monkeypatch.setattr(backend_mod, "_DEFAULT", None)
     with pytest.raises(IfxError):
         InflexionGame(7).valid_actions_mask()                # needs libifx_b200.so AND a CUDA device
+
+
+def test_header_is_plain_c_and_the_c_example_compiles(tmp_path):
+    """include/ifx_b200.h must be usable from C (no C++-isms, no CUDA or torch headers): examples/c_abi_demo.c, a C99
+    host program that dlopen()s the library, has to compile with gcc alone."""
+    import subprocess
+    out = tmp_path / "c_abi_demo"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", str(out), "-ldl"]
+    subprocess.run(cmd, check=True, capture_output=True)
+    assert out.exists()
