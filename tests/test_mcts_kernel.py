@@ -322,6 +322,8 @@ def test_zero_sized_calls_are_noops(backend):
 def test_maximum_pool_size(backend):
     """nodes_per_game at its maximum (16 383 slots: the 14-bit child hint) gives the same search as the default pool;
     one slot more is rejected by the library."""
+    if backend.is_cuda:
+        pytest.skip("added after this round's GPU budget ended: runs on the CPU build of the kernels only, so far")
     out = []
     for nodes in (None, 16383):
         m = BatchedMCTS(1, 30, 1.0, seed=3, backend=backend, nodes_per_game=nodes)
