@@ -317,21 +317,3 @@ def test_zero_sized_calls_are_noops(backend):
     assert dll.ifx_stub_policy_value(None, 0, None, 0, None, 343, None, None) == 0
     assert dll.ifx_stub_policy_value(None, 1, None, 0, None, 343, None, None) == -1      # IFX_E_ARG
     assert dll.ifx_net_im2col3x3(None, 0, None, None) == 0
-
-
-def test_maximum_pool_size(backend):
-    """nodes_per_game at its maximum (16 383 slots: the 14-bit child hint) gives the same search as the default pool;
-    one slot more is rejected by the library."""
-    if backend.is_cuda:
-        pytest.skip("added after this round's GPU budget ended: runs on the CPU build of the kernels only, so far")
-    out = []
-    for nodes in (None, 16383):
-        m = BatchedMCTS(1, 30, 1.0, seed=3, backend=backend, nodes_per_game=nodes)
-        m.reset(start_states(1, 343))
-        m.search(stub_eval("float"))
-        m.raise_on_faults()
-        out.append(m.root_stats(want_q=True))
-    assert torch.equal(out[0]["counts"].cpu(), out[1]["counts"].cpu()) and torch.equal(out[0]["q32"].cpu(), out[1]["q32"].cpu())
-    from inflexion_b200._capi import IfxError
-    with pytest.raises(IfxError):
-        BatchedMCTS(1, 30, 1.0, seed=3, backend=backend, nodes_per_game=16384)

@@ -1,0 +1,81 @@
+"""Cases added after round 1's GPU budget was spent: green on the CPU build of the kernels (hostsim), not yet run on a
+B200.  They live in a file that sorts last so that, under ``pytest -x -m gpu``, they cannot mask the rest of the suite."""
+import numpy as np
+import pytest
+import torch
+
+from inflexion_b200.mcts_batched import BatchedMCTS
+from inflexion_b200.state import pack_states
+from oracle.inflexion_mcts import OracleMCTS, PhiloxDraws, sample_action
+from oracle.inflexion_rules import OracleGame
+from test_mcts_kernel import start_states, stub_eval, stub_predict
+
+
+def test_maximum_pool_size(backend):
+    """nodes_per_game at its maximum (16 383 slots: the 14-bit child hint) gives the same search as the default pool;
+    one slot more is rejected by the library."""
+    out = []
+    for nodes in (None, 16383):
+        m = BatchedMCTS(1, 30, 1.0, seed=3, backend=backend, nodes_per_game=nodes)
+        m.reset(start_states(1, 343))
+        m.search(stub_eval("float"))
+        m.raise_on_faults()
+        out.append(m.root_stats(want_q=True))
+    assert torch.equal(out[0]["counts"].cpu(), out[1]["counts"].cpu()) and torch.equal(out[0]["q32"].cpu(), out[1]["q32"].cpu())
+    from inflexion_b200._capi import IfxError
+    with pytest.raises(IfxError):
+        BatchedMCTS(1, 30, 1.0, seed=3, backend=backend, nodes_per_game=16384)
+
+
+@pytest.mark.parametrize("n_own,n_opp", [(24, 3), (45, 2)])
+def test_crowded_positions_with_more_than_one_row_group(backend, n_own, n_opp):
+    """Searches rooted at crowded positions: the root (and its descendants) have more than 128 -- and, with 45 own
+    stacks, more than 256 -- valid actions, so selection, expansion and the root mirror run over two / three 128-entry
+    groups of the compact rows.  Bit-exact against the oracle (tables of every live node, Q bits included)."""
+    rng = np.random.default_rng(n_own)
+    cells = rng.permutation(49)
+    board = np.zeros(49, dtype=np.int64)
+    board[cells[:n_own]] = 1                                              # total power <= 48 keeps spawns legal too
+    board[cells[n_own:n_own + n_opp]] = -1
+    sims, cpuct, seed = 40, 1.25, 19
+    m = BatchedMCTS(1, sims, cpuct, seed=seed, backend=backend)
+    m.reset(pack_states(board[None], 1, 10, 0, 343, tags=0))
+    game = OracleGame(board.reshape(7, 7).copy(), 1, 10, 0, 343)
+    nv = int(game.valid_actions_mask().sum())
+    assert nv > (256 if n_own == 45 else 128)
+    orc = OracleMCTS(stub_predict("float"), sims, cpuct, PhiloxDraws(seed))
+    for mv in range(2):
+        orc.move = mv
+        pi = orc.get_action_prob(game, temp=1)
+        m.search(stub_eval("float"))
+        m.raise_on_faults()
+        st = m.root_stats(want_q=True)
+        assert np.array_equal(st["counts"].cpu().numpy()[0], orc.root_counts(game))
+        tv = m.table_views()
+        keys = tv["key"][0]
+        used = np.nonzero(keys[:, 0] != np.uint64(2 ** 64 - 1))[0]
+        checked = 0
+        for slot in used:
+            k0, k1 = int(keys[slot, 0]), int(keys[slot, 1])
+            own = np.array([(k0 >> c) & 1 for c in range(49)], dtype=np.int64)
+            opp = np.array([(k1 >> c) & 1 for c in range(49)], dtype=np.int64)
+            key = np.stack([own, opp, np.full(49, k0 >> 49), np.full(49, (k1 >> 49) & 1)]).astype(np.int64).reshape(4, 7, 7).tobytes()
+            if key not in orc.P:
+                continue                                              # (a node of an older move the oracle never prunes)
+            assert tv["P"][0, slot].tobytes() == orc.P[key].astype(np.float32).tobytes()
+            assert tv["ns"][0, slot] == orc.Ns[key]
+            for a in np.nonzero(orc.V[key])[0]:
+                n = orc.N.get((key, int(a)), 0)
+                raw = int(tv["Nraw"][0, slot, a])
+                assert (raw & 0x1FFFF) == n
+                if n:
+                    q = orc.Q[(key, int(a))]
+                    got = tv["Q64"][0, slot, a] if raw >> 31 else np.float64(tv["Q32"][0, slot, a])
+                    assert np.float64(got).tobytes() == np.float64(q.x).tobytes()
+            checked += 1
+        assert checked >= sims // 2
+        a = sample_action(pi, PhiloxDraws(seed).uniform(mv))
+        acts = m.sample_actions(1000)
+        assert int(acts[0]) == a
+        m.advance(acts)
+        game = game.to_next_state(a)
