@@ -37,3 +37,12 @@ def backend(request):
 def cuda_backend():
     from inflexion_b200.backend import Backend
     return Backend.cuda()
+
+
+@pytest.hookimpl(trylast=True)
+def pytest_collection_modifyitems(config, items):
+    """Keep tests/test_zz_late_additions.py (cases not yet run on a GPU) at the very end, also after pytest has grouped
+    the tests by the session-scoped ``backend`` parameter, so that ``-x`` cannot let them mask the rest of the suite."""
+    late = [it for it in items if "test_zz_late_additions" in it.nodeid]
+    if late:
+        items[:] = [it for it in items if "test_zz_late_additions" not in it.nodeid] + late
