@@ -199,6 +199,8 @@ def workload_config(a, per_gpu_games, note=None):
     cfg = {"workload": f"batched Inflexion self-play, {per_gpu_games} concurrent games x {a.sims} sims/move per GPU, "
                        f"{a.net} net, 7x7 board, max_turns=343, cpuct=1, tempThreshold=30",
            "games_per_gpu": per_gpu_games, "sims_per_move": a.sims, "net": a.net,
+           "arithmetic": "tree: float32 with numpy's exact operation order (float64 where the reference's Python floats are)"
+                         + ("; net: fp16 inputs/weights, fp32 accumulate" if a.net == "default" else "; net: integer-hash stub"),
            "l2_policy": "working set (node pools) far larger than L2; no flush needed",
            "parallelism": f"games sharded over {a.gpus} GPU(s), no collective"}
     if note:
@@ -364,7 +366,7 @@ def run_ours(a):
         line = {
             "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 tree arithmetic (bit-exact numpy semantics); fp16 net, fp32 accumulate" if a.net == "default" else "f32",
+            "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "games_per_s": value / (a.sims * MOVES_PER_GAME),
             "config": workload_config(a, a.games),
             "roofline": {"kernel": "tree_wave_kernel", "bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s",
