@@ -92,6 +92,14 @@ class NNetWrapper(NeuralNet):
             history.append((pi_losses.avg, v_losses.avg))
             if verbose:
                 print(f"  Loss_pi={pi_losses} Loss_v={v_losses}")
+        if dist and world > 1:
+            # BatchNorm running statistics are computed from rank-local batches: average them so that every rank
+            # leaves train() with the SAME net (parameters already agree through the all-reduced gradients) -- the
+            # ranks play the next iteration's games with it and rank 0 writes the checkpoint for all of them
+            for name, buf in self.nnet.named_buffers():
+                if buf.dtype.is_floating_point:
+                    dist.all_reduce(buf)
+                    buf /= world
         self._folded = None
         return history
 

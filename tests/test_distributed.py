@@ -74,7 +74,8 @@ def _train_worker(rank, world, port, out_dir):
     pis = np.full((n, 343), 1.0 / 343)
     examples = [(planes[i], pis[i].tolist(), float((-1) ** (i + rank))) for i in range(n)]
     w.train(examples, verbose=False)
-    flat = torch.cat([p.detach().reshape(-1) for p in w.nnet.parameters()])
+    # parameters AND buffers (BatchNorm running statistics): the whole state a checkpoint holds
+    flat = torch.cat([t.detach().reshape(-1).float() for t in w.nnet.state_dict().values()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     if rank == 0:
