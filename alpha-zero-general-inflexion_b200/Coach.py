@@ -85,15 +85,18 @@ class Coach:
         fused = hasattr(self.nnet, "predict_head") and getattr(getattr(self.nnet, "device", None), "type", "cpu") == "cuda"
         return (self.nnet.predict_head if fused else self.nnet.predict_batch), fused
 
-    def selfPlayBatch(self, num_games: int, seed: int = 0, game_id_base: int = 0, gather: bool = False):
+    def selfPlayBatch(self, num_games: int, seed: int = 0, game_id_base: int = 0, gather: bool = False,
+                      compact: bool = False):
         """``num_games`` episodes at once on the device -> list of (planes, pi list, v) in the reference's order.
 
         Under torch.distributed the games shard by rank in contiguous blocks (game i plays the same game whichever
         rank owns it; no collective during self-play) and every rank returns the examples of ITS games -- they stay
         rank-local and ``NNetWrapper.train`` all-reduces the gradients.  ``gather``: every rank
         returns the examples of ALL games instead (one all-gather of the un-expanded records, the "final example
-        gather"; the 36-fold expansion happens after it)."""
-        from .selfplay import SelfPlayEngine, build_examples
+        gather"; the 36-fold expansion happens after it).  ``compact``: return a ``selfplay.ExampleSet`` (same
+        examples, expanded on demand per training batch) instead of the materialised list -- 1.5 KB per move instead
+        of 19 MB per game, which is what lets an iteration hold thousands of games."""
+        from .selfplay import ExampleSet, SelfPlayEngine, build_examples
         rank, world = self._dist()
         per = -(-int(num_games) // world)
         if world > 1 and per * world != num_games:
@@ -108,7 +111,10 @@ class Coach:
         else:
             eng.play_episode()
         eng.mcts.raise_on_faults()
-        planes, pi, v = build_examples(eng.be, eng.gather_records()) if gather else eng.examples()
+        rec = eng.gather_records() if gather else eng.records()
+        if compact:
+            return ExampleSet(eng.be, rec)
+        planes, pi, v = build_examples(eng.be, rec)
         return [(planes[i], pi[i].tolist(), float(v[i])) for i in range(len(v))]
 
     def learn(self):
@@ -116,21 +122,31 @@ class Coach:
         for i in range(1, self.args.numIters + 1):
             log.info(f"Starting Iter #{i} ...")
             rank, world = self._dist()
+            opts = dict(self.args)
+            compact = bool(opts.get("compactExamples", False))     # keep un-expanded records (selfplay.ExampleSet)
             if not self.skipFirstSelfPlay or i > 1:
-                examples = deque([], maxlen=self.args.maxlenOfQueue)
-                examples += self.selfPlayBatch(int(self.args.numEps), seed=self._job_seed(),
-                                               gather=bool(dict(self.args).get("gatherExamples", False)))
-                self.trainExamplesHistory.append(examples)
+                new = self.selfPlayBatch(int(self.args.numEps), seed=self._job_seed(),
+                                         gather=bool(opts.get("gatherExamples", False)), compact=compact)
+                if compact:
+                    self.trainExamplesHistory.append(new)
+                else:
+                    examples = deque([], maxlen=self.args.maxlenOfQueue)
+                    examples += new
+                    self.trainExamplesHistory.append(examples)
             if len(self.trainExamplesHistory) > self.args.numItersForTrainExamplesHistory:
                 log.warning(f"Removing the oldest entry in trainExamples. len(trainExamplesHistory) = "
                             f"{len(self.trainExamplesHistory)}")
                 self.trainExamplesHistory.pop(0)
-            self.saveTrainExamples(i - 1)
-            train_examples = []
-            for e in self.trainExamplesHistory:
-                train_examples.extend(e)
-            shuffle(train_examples)
-            self.nnet.train(train_examples)
+            if compact:                                            # (record files are not in the reference's format:
+                from .selfplay import ExampleUnion                  # compact mode trades the .examples file for scale)
+                self.nnet.train(ExampleUnion(self.trainExamplesHistory))
+            else:
+                self.saveTrainExamples(i - 1)
+                train_examples = []
+                for e in self.trainExamplesHistory:
+                    train_examples.extend(e)
+                shuffle(train_examples)
+                self.nnet.train(train_examples)
             if rank == 0:
                 self.nnet.save_checkpoint(folder=self.args.checkpoint, filename="temp.pth.tar")
             if i % pit_interval != 0:

@@ -46,9 +46,13 @@ class NNetWrapper(NeuralNet):
         dist = torch.distributed if torch.distributed.is_available() and torch.distributed.is_initialized() else None
         world = dist.get_world_size() if dist else 1
         optimizer = optim.Adam(self.nnet.parameters())
-        boards_all = torch.as_tensor(np.array([e[0] for e in examples]).astype(np.float32))
-        pis_all = torch.as_tensor(np.array([e[1] for e in examples], dtype=np.float32))
-        vs_all = torch.as_tensor(np.array([e[2] for e in examples], dtype=np.float32))
+        # ``examples`` is the reference's list of (planes, pi, v), or an on-demand set (selfplay.ExampleSet /
+        # ExampleUnion: ``len`` + ``batch(ids)``) that expands only the rows a batch draws
+        on_demand = hasattr(examples, "batch")
+        if not on_demand:
+            boards_all = torch.as_tensor(np.array([e[0] for e in examples]).astype(np.float32))
+            pis_all = torch.as_tensor(np.array([e[1] for e in examples], dtype=np.float32))
+            vs_all = torch.as_tensor(np.array([e[2] for e in examples], dtype=np.float32))
         params = [p for p in self.nnet.parameters() if p.requires_grad]
         # steps per epoch: one pass over the examples (NNet.py:50).  Under torch.distributed the examples are
         # rank-local and their number differs from rank to rank (games end at different moves), so every rank must
@@ -69,10 +73,14 @@ class NNetWrapper(NeuralNet):
             self.nnet.train()
             pi_losses, v_losses = AverageMeter(), AverageMeter()
             for _ in range(steps):
-                ids = torch.from_numpy(np.random.randint(len(examples), size=args.batch_size))
-                boards = boards_all[ids].to(self.device, non_blocking=True)
-                target_pis = pis_all[ids].to(self.device, non_blocking=True)
-                target_vs = vs_all[ids].to(self.device, non_blocking=True)
+                ids = np.random.randint(len(examples), size=args.batch_size)
+                if on_demand:
+                    boards, target_pis, target_vs = (t.to(self.device) for t in examples.batch(ids))
+                else:
+                    ids = torch.from_numpy(ids)
+                    boards = boards_all[ids].to(self.device, non_blocking=True)
+                    target_pis = pis_all[ids].to(self.device, non_blocking=True)
+                    target_vs = vs_all[ids].to(self.device, non_blocking=True)
                 out_pi, out_v = self.nnet(boards)
                 l_pi = self.loss_pi(target_pis, out_pi)
                 l_v = self.loss_v(target_vs, out_v)

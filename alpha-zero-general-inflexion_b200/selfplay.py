@@ -272,3 +272,128 @@ def build_examples(be, rec: dict, games=None, fix_alignment: bool = False, expan
         planes = rules.symmetries(planes.contiguous(), backend=be).reshape(-1, 4, 7, 7)
         pi = rules.symmetries(pi.reshape(-1, 7, 7, 7).contiguous(), backend=be).reshape(-1, 343)
     return planes.cpu().numpy(), pi.cpu().numpy(), np.concatenate(values)
+
+
+def _sym36_code(form: np.ndarray) -> np.ndarray:
+    """Index 0..35 in the order of InflexionGame.symmetries (InflexionGame.py:102-113) -> symmetry code k + 6*shift
+    (axis 'r'): identity, rotations 1..5, then for k = 1..5 the translations j = 1..6 of rotation k."""
+    form = np.asarray(form)
+    k, j = (form - 6) // 6 + 1, (form - 6) % 6 + 1
+    return np.where(form < 6, form, k + 6 * j).astype(np.int32)
+
+
+class ExampleSet:
+    """The training examples of a self-play record WITHOUT materialising them.
+
+    ``build_examples`` expands every recorded move into its 36 symmetric forms (1.6 KB each as arrays, far more as the
+    reference's Python lists): 19 MB per game, 637 GB for BASELINE config 4's 32 768 games.  An
+    ``ExampleSet`` keeps the un-expanded record (1.5 KB per move) plus an index of the finished episodes and produces
+    any batch of expanded examples on demand -- ``batch(idx)`` returns exactly rows ``idx`` of what ``build_examples``
+    would return (same order, same symmetry, same value targets incl. the reference's alignment quirk D1), computed
+    for that batch only by the rules kernels.  ``NNetWrapper.train`` accepts it in place of the example list, which
+    makes its uniform sampling with replacement (NNet.py:52) the same distribution at O(record) memory."""
+
+    def __init__(self, be, rec: dict, games=None, fix_alignment: bool = False):
+        self.be = be
+        self.temp_threshold = int(rec["temp_threshold"])
+        ex_states, ex_after, ex_counts, ex_actions = rec["states"], rec["after"], rec["counts"], rec["actions"]
+        n_moves, G = ex_actions.shape[0], ex_actions.shape[1]
+        st_all = ex_states.cpu().numpy().view(STATE_DTYPE).reshape(n_moves, G)
+        after_all = ex_after.cpu().numpy().view(STATE_DTYPE).reshape(n_moves, G)
+        acts_all = ex_actions.cpu().numpy()
+        value_of = {0: 0.0, 1: 1e-4, 2: 1.0, 3: -1.0}
+        mv, gg, ep_move, ep_first, ep_len, mover, end_player, result = [], [], [], [], [], [], [], []
+        total = 0
+        for g in (range(G) if games is None else games):
+            start = 0
+            for m in range(n_moves):
+                if acts_all[m, g] < 0:
+                    start = m + 1
+                    continue
+                if after_all[m, g]["outcome"] == 0:
+                    continue
+                rows = np.arange(start, m + 1)
+                start = m + 1
+                n = len(rows)
+                final = after_all[m, g]
+                mv.append(rows); gg.append(np.full(n, g)); ep_move.append(np.arange(n))
+                ep_first.append(np.full(n, total)); ep_len.append(np.full(n, n))
+                mover.append(np.where(st_all[rows, g]["player"] == 0, 1, -1))
+                end_player.append(np.full(n, 1 if final["player"] == 0 else -1))
+                result.append(np.full(n, value_of[int(final["outcome"])]))
+                total += n
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)  # noqa: E731
+        self.mv, self.g, self.ep_move = cat(mv, np.int64), cat(gg, np.int64), cat(ep_move, np.int64)
+        self.ep_first, self.ep_len = cat(ep_first, np.int64), cat(ep_len, np.int64)
+        self.mover, self.end_player, self.result = cat(mover, np.int64), cat(end_player, np.int64), cat(result, np.float64)
+        self.fix_alignment = bool(fix_alignment)
+        # only the selected (move, game) pairs are kept, on the device: states 64 B + counts 1 372 B + action 4 B each
+        dev = be.device
+        mi, gi = torch.from_numpy(self.mv).to(dev), torch.from_numpy(self.g).to(dev)
+        self.states = ex_states[mi, gi].contiguous()
+        self.counts = ex_counts[mi, gi].contiguous()
+        self.actions = ex_actions[mi, gi].contiguous()
+
+    def __len__(self) -> int:
+        return 36 * len(self.mv)
+
+    def _values(self, rec_idx: np.ndarray, form: np.ndarray) -> np.ndarray:
+        """Value target of expanded example (record rec_idx, symmetric form) -- Coach.py:89-90 with players[] as the
+        reference builds it (Coach.py:79: extended by the CUMULATIVE example count)."""
+        if self.fix_alignment:
+            player = self.mover[rec_idx]
+        else:
+            li = 36 * self.ep_move[rec_idx] + form                     # position inside the episode's example list
+            # players = [mover_0]*36 + [mover_1]*72 + [mover_2]*108 + ...: entry li belongs to the j with
+            # 18 j (j+1) <= li < 18 (j+1)(j+2)
+            j = ((np.sqrt(1.0 + 4.0 * li / 18.0) - 1.0) / 2.0).astype(np.int64)
+            j = np.where(18 * (j + 1) * (j + 2) <= li, j + 1, j)
+            j = np.where(18 * j * (j + 1) > li, j - 1, j)
+            player = self.mover[self.ep_first[rec_idx] + j]
+        return np.where(player == self.end_player[rec_idx], self.result[rec_idx], -self.result[rec_idx])
+
+    def batch(self, idx, planes_dtype=torch.float32, target_dtype=torch.float32):
+        """Rows ``idx`` (any order, repeats allowed) of the expanded example list ->
+        (planes [B,4,7,7] planes_dtype, pi target_dtype [B,343], v target_dtype [B]) on the device."""
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        rec_idx, form = idx // 36, idx % 36
+        dev = self.be.device
+        ri = torch.from_numpy(rec_idx).to(dev)
+        sym = torch.from_numpy(_sym36_code(form)).to(dev)
+        planes = rules.planes(self.states[ri].contiguous(), sym=sym, dtype=planes_dtype, backend=self.be)
+        counts = self.counts[ri].to(torch.float64)
+        pi = counts / counts.sum(dim=1, keepdim=True)                                    # MCTS.py:58-60 at temp 1
+        onehot = torch.zeros_like(pi)
+        onehot[torch.arange(len(idx), device=dev), self.actions[ri].long()] = 1.0          # MCTS.py:51-56 at temp 0
+        temp1 = torch.from_numpy((self.ep_move[rec_idx] + 1) < self.temp_threshold).to(dev)
+        pi = torch.where(temp1[:, None], pi, onehot)
+        pi = rules.transform(pi.reshape(-1, 7, 7, 7).contiguous(), sym, backend=self.be).reshape(-1, 343)
+        v = torch.from_numpy(self._values(rec_idx, form)).to(dev)
+        return planes, pi.to(target_dtype), v.to(target_dtype)
+
+    def materialise(self):
+        """The full expanded set as ``build_examples`` returns it (tests; small sets only)."""
+        planes, pi, v = self.batch(np.arange(len(self)), planes_dtype=torch.int64, target_dtype=torch.float64)
+        return planes.cpu().numpy(), pi.cpu().numpy(), v.cpu().numpy()
+
+
+class ExampleUnion:
+    """Several ``ExampleSet``s (the iterations of Coach.trainExamplesHistory) addressed as one example list."""
+
+    def __init__(self, sets):
+        self.sets = [s for s in sets if len(s)]
+        self.offsets = np.cumsum([0] + [len(s) for s in self.sets])
+
+    def __len__(self) -> int:
+        return int(self.offsets[-1])
+
+    def batch(self, idx, planes_dtype=torch.float32, target_dtype=torch.float32):
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        which = np.searchsorted(self.offsets, idx, side="right") - 1
+        outs, order = [], []
+        for k in np.unique(which):
+            sel = np.nonzero(which == k)[0]
+            outs.append(self.sets[k].batch(idx[sel] - self.offsets[k], planes_dtype, target_dtype))
+            order.append(sel)
+        inv = torch.from_numpy(np.argsort(np.concatenate(order))).to(outs[0][0].device)
+        return tuple(torch.cat([o[i] for o in outs])[inv] for i in range(3))

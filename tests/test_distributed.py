@@ -158,6 +158,11 @@ def _learn_worker(rank, world, port, out_dir):
     coach = Coach(game, nnet, args)
     coach.learn()                                            # self-play (2 games per rank) -> train (all-reduce) -> checkpoint
     n_local = sum(len(d) for d in coach.trainExamplesHistory)
+    # a second iteration in compact mode: un-expanded records, examples expanded per training batch
+    args["compactExamples"] = True
+    compact_coach = Coach(game, nnet, args)
+    compact_coach.learn()
+    assert len(compact_coach.trainExamplesHistory) == 1 and len(compact_coach.trainExamplesHistory[0]) % 36 == 0
     flat = torch.cat([p.detach().reshape(-1) for p in nnet.nnet.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)

@@ -8,6 +8,8 @@ from inflexion_b200.mcts_batched import BatchedMCTS
 from inflexion_b200.state import pack_states
 from oracle.inflexion_mcts import OracleMCTS, PhiloxDraws, sample_action
 from oracle.inflexion_rules import OracleGame
+from inflexion_b200.selfplay import SelfPlayEngine
+from inflexion_b200.stubnet import stub_policy_value
 from test_mcts_kernel import start_states, stub_eval, stub_predict
 
 
@@ -79,3 +81,34 @@ def test_crowded_positions_with_more_than_one_row_group(backend, n_own, n_opp):
         assert int(acts[0]) == a
         m.advance(acts)
         game = game.to_next_state(a)
+
+
+@pytest.mark.parametrize("fix_alignment", [False, True])
+def test_example_set_equals_the_expanded_examples(backend, fix_alignment):
+    """ExampleSet produces any row of the expanded example list on demand, bit-identical to build_examples (order,
+    symmetric form, temperature rule, value targets incl. the reference's alignment quirk) without materialising it."""
+    from inflexion_b200.selfplay import ExampleSet, build_examples
+    eng = SelfPlayEngine(5, 10, lambda x: stub_policy_value(x), temp_threshold=3, seed=11, max_turns=6, backend=backend)
+    eng.play_episode()
+    planes, pi, v = build_examples(backend, eng.records(), fix_alignment=fix_alignment)
+    es = ExampleSet(backend, eng.records(), fix_alignment=fix_alignment)
+    assert len(es) == len(v) > 36 * 5
+    p2, pi2, v2 = es.materialise()
+    assert np.array_equal(p2, planes) and pi2.tobytes() == pi.tobytes() and v2.tobytes() == v.tobytes()
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, len(es), size=97)                  # a batch as NNetWrapper.train draws it (with replacement)
+    pb, pib, vb = es.batch(idx)
+    assert pb.dtype == torch.float32 and np.array_equal(pb.cpu().numpy(), planes[idx].astype(np.float32))
+    assert np.array_equal(pib.cpu().numpy(), pi[idx].astype(np.float32)) and np.array_equal(vb.cpu().numpy(), v[idx].astype(np.float32))
+    sub = ExampleSet(backend, eng.records(), games=[1, 3], fix_alignment=fix_alignment)
+    ps, _, vs = build_examples(backend, eng.records(), games=[1, 3], fix_alignment=fix_alignment)
+    assert len(sub) == len(vs) and np.array_equal(sub.materialise()[0], ps)
+    # several sets addressed as one list (Coach.trainExamplesHistory in compact mode)
+    from inflexion_b200.selfplay import ExampleUnion
+    uni = ExampleUnion([es, sub])
+    assert len(uni) == len(es) + len(sub)
+    idx = rng.integers(0, len(uni), size=64)
+    pu, piu, vu = uni.batch(idx)
+    all_planes = np.concatenate([planes, ps]).astype(np.float32)
+    all_v = np.concatenate([v, vs]).astype(np.float32)
+    assert np.array_equal(pu.cpu().numpy(), all_planes[idx]) and np.array_equal(vu.cpu().numpy(), all_v[idx])
