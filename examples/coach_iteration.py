@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--arena", type=int, default=20)
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--gather", action="store_true", help="all-gather the un-expanded self-play records (final example gather)")
+    ap.add_argument("--compact", action="store_true",
+                    help="keep un-expanded records and expand examples per training batch (selfplay.ExampleSet): thousands of games")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -45,7 +47,7 @@ def main():
     coach = Coach(game, nnet, dotdict({"numMCTSSims": a.sims, "cpuct": 1, "tempThreshold": 30, "numEps": a.games * world}))
 
     t0 = time.time()
-    examples = coach.selfPlayBatch(a.games * world, seed=1, gather=a.gather)   # this rank's games (all games with --gather)
+    examples = coach.selfPlayBatch(a.games * world, seed=1, gather=a.gather, compact=a.compact)   # this rank's games (all with --gather)
     torch.cuda.synchronize()
     t1 = time.time()
     moves = a.max_turns + 1
