@@ -42,7 +42,10 @@ class NNetWrapper(NeuralNet):
     def train(self, examples, verbose=True):
         """examples: list of (planes, pi, v).  Adam with default lr (the reference never passes args.lr,
         NNet.py:40), ``epochs`` x ``len/batch`` steps, each batch drawn WITH replacement (NNet.py:52).
-        Under torch.distributed every rank draws its own batch and gradients are averaged (all-reduce)."""
+        Under torch.distributed the GLOBAL batch stays ``batch_size`` (each rank draws batch_size/world rows from its own
+        examples), gradients are averaged by a bucketed all-reduce overlapped with backward, and on GPUs BatchNorm uses
+        the statistics of the global batch -- one data-parallel step is the reference's step on the union of the
+        ranks' draws."""
         dist = torch.distributed if torch.distributed.is_available() and torch.distributed.is_initialized() else None
         world = dist.get_world_size() if dist else 1
         optimizer = optim.Adam(self.nnet.parameters())
@@ -53,19 +56,47 @@ class NNetWrapper(NeuralNet):
             boards_all = torch.as_tensor(np.array([e[0] for e in examples]).astype(np.float32))
             pis_all = torch.as_tensor(np.array([e[1] for e in examples], dtype=np.float32))
             vs_all = torch.as_tensor(np.array([e[2] for e in examples], dtype=np.float32))
-        params = [p for p in self.nnet.parameters() if p.requires_grad]
         # steps per epoch: one pass over the examples (NNet.py:50).  Under torch.distributed the examples are
         # rank-local and their number differs from rank to rank (games end at different moves), so every rank must
         # agree on the count or the gradient all-reduce deadlocks: one pass over the GLOBAL set at a global batch of
         # world x batch_size.
         n_total = len(examples)
+        per_rank_batch = args.batch_size
         if dist and world > 1:
-            t = torch.tensor([n_total], dtype=torch.int64, device=self.device)
-            dist.all_reduce(t)
-            n_total = int(t[0])
-            if len(examples) == 0:
-                raise ValueError("NNetWrapper.train: this rank has no examples")
-        steps = int(n_total / (args.batch_size * world))
+            # (i) every rank must enter with the SAME net: parameters and buffers are broadcast from rank 0 (nothing else
+            # guarantees it -- NNetWrapper.__init__ is randomly initialised per process);
+            for t in list(self.nnet.parameters()) + list(self.nnet.buffers()):
+                dist.broadcast(t.data, 0)
+            # gradients: bucketed all-reduce (mean) overlapped with the backward pass (DistributedDataParallel: NCCL over
+            # NVLink on GPUs, gloo in the CPU tests).  On GPUs the BatchNorm layers become SyncBatchNorm for the length of
+            # train(), so batch statistics are those of the GLOBAL batch, as in the reference's single process
+            # (NNet.py:52,58); the original modules (sharing the same tensors) are put back at the end.
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            swapped = {}
+            if self.device.type == "cuda":
+                for name, mod in list(self.nnet.named_children()):
+                    if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                        swapped[name] = mod
+                        setattr(self.nnet, name, torch.nn.SyncBatchNorm.convert_sync_batchnorm(mod))
+            model = DDP(self.nnet, device_ids=[self.device.index] if self.device.type == "cuda" else None,
+                        broadcast_buffers=False, gradient_as_bucket_view=True, bucket_cap_mb=8)
+            # (ii) the step count and the "a rank has no examples" error are decided COLLECTIVELY, so that all ranks
+            # raise together instead of one raising while the others hang in the first gradient all-reduce;
+            t = torch.tensor([n_total, -n_total], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t[:1])
+            dist.all_reduce(t[1:], op=dist.ReduceOp.MAX)
+            n_total, n_min = int(t[0]), -int(t[1])
+            if n_min == 0:
+                raise ValueError("NNetWrapper.train: a rank has no examples")
+            # (iii) the reference's schedule is kept: GLOBAL batch = batch_size (NNet.py:21,52), i.e. batch_size/world
+            # rows per rank, Adam's lr unchanged, steps = global examples / batch_size per epoch (NNet.py:50).
+            # ``args.dp_global_batch`` (optional) overrides the global batch for runs that want larger steps.
+            global_batch = int(args.get("dp_global_batch") or args.batch_size)
+            per_rank_batch = max(1, global_batch // world)
+            steps = int(n_total / (per_rank_batch * world))
+        else:
+            steps = int(n_total / args.batch_size)
+            model, swapped = self.nnet, {}
         history = []
         for epoch in range(args.epochs):
             if verbose:
@@ -73,7 +104,7 @@ class NNetWrapper(NeuralNet):
             self.nnet.train()
             pi_losses, v_losses = AverageMeter(), AverageMeter()
             for _ in range(steps):
-                ids = np.random.randint(len(examples), size=args.batch_size)
+                ids = np.random.randint(len(examples), size=per_rank_batch)
                 if on_demand:
                     boards, target_pis, target_vs = (t.to(self.device) for t in examples.batch(ids))
                 else:
@@ -81,19 +112,11 @@ class NNetWrapper(NeuralNet):
                     boards = boards_all[ids].to(self.device, non_blocking=True)
                     target_pis = pis_all[ids].to(self.device, non_blocking=True)
                     target_vs = vs_all[ids].to(self.device, non_blocking=True)
-                out_pi, out_v = self.nnet(boards)
+                out_pi, out_v = model(boards)
                 l_pi = self.loss_pi(target_pis, out_pi)
                 l_v = self.loss_v(target_vs, out_v)
-                optimizer.zero_grad()
-                (l_pi + l_v).backward()
-                if dist and world > 1:
-                    flat = torch.cat([p.grad.reshape(-1) for p in params])
-                    dist.all_reduce(flat)
-                    flat /= world
-                    off = 0
-                    for p in params:
-                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                        off += p.numel()
+                optimizer.zero_grad(set_to_none=False)
+                (l_pi + l_v).backward()                      # (DDP: the gradient buckets are all-reduced while this runs)
                 optimizer.step()
                 pi_losses.update(l_pi.item(), boards.size(0))
                 v_losses.update(l_v.item(), boards.size(0))
@@ -104,10 +127,15 @@ class NNetWrapper(NeuralNet):
             # BatchNorm running statistics are computed from rank-local batches: average them so that every rank
             # leaves train() with the SAME net (parameters already agree through the all-reduced gradients) -- the
             # ranks play the next iteration's games with it and rank 0 writes the checkpoint for all of them
-            for name, buf in self.nnet.named_buffers():
-                if buf.dtype.is_floating_point:
-                    dist.all_reduce(buf)
-                    buf /= world
+            # (with SyncBatchNorm they already agree; averaging identical values is a no-op up to rounding)
+            if not swapped:
+                for name, buf in self.nnet.named_buffers():
+                    if buf.dtype.is_floating_point:
+                        dist.all_reduce(buf)
+                        buf /= world
+            for name, mod in swapped.items():              # plain BatchNorm modules back (they share the trained tensors)
+                setattr(self.nnet, name, mod)
+            del model
         self._folded = None
         return history
 

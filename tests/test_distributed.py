@@ -66,7 +66,7 @@ def _train_worker(rank, world, port, out_dir):
     from inflexion_b200.inflexion.pytorch import NNet as nnet_mod
     from test_nnet import Shape, random_planes
     nnet_mod.args.update(cuda=False, epochs=2, batch_size=16, num_channels=8)
-    torch.manual_seed(0)                                     # same initial weights on every rank
+    torch.manual_seed(rank)                                  # DIFFERENT initial weights per rank: train() must broadcast rank 0's
     w = nnet_mod.NNetWrapper(Shape(), device="cpu", infer_dtype=torch.float32)
     np.random.seed(100 + rank)                               # different batches per rank
     n = 48 + 40 * rank                                       # rank-local example counts differ (games end at different
@@ -78,16 +78,25 @@ def _train_worker(rank, world, port, out_dir):
     flat = torch.cat([t.detach().reshape(-1).float() for t in w.nnet.state_dict().values()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
+    # a rank without examples: EVERY rank must raise (decided collectively), nobody may hang in an all-reduce
+    raised = 0
+    try:
+        w.train([] if rank == 1 else examples, verbose=False)
+    except ValueError:
+        raised = 1
+    flags = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([raised]))
     if rank == 0:
-        torch.save(gathered, os.path.join(out_dir, "weights.pt"))
+        torch.save(gathered + [torch.cat(flags)], os.path.join(out_dir, "weights.pt"))
     dist.destroy_process_group()
 
 
 def test_data_parallel_training_keeps_ranks_in_sync(tmp_path):
     port = _free_port()
     mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    w0, w1 = torch.load(os.path.join(tmp_path, "weights.pt"))
-    assert torch.equal(w0, w1)                               # identical updates from all-reduced gradients
+    w0, w1, raised = torch.load(os.path.join(tmp_path, "weights.pt"))
+    assert torch.equal(w0, w1)                               # identical nets although the ranks started from different ones
+    assert raised.tolist() == [1, 1]                         # the empty-rank error is raised on every rank
     assert float(w0.abs().sum()) > 0
 
 
@@ -148,7 +157,7 @@ def _learn_worker(rank, world, port, out_dir):
     from inflexion_b200.utils import dotdict
     backend_mod._DEFAULT = hostsim_backend()                 # test seam: the kernels' logic-check build on the CPU
     nnet_mod.args.update(cuda=False, epochs=1, batch_size=32, num_channels=8)
-    torch.manual_seed(0)                                     # same initial weights on every rank
+    torch.manual_seed(rank)                                  # DIFFERENT initial weights per rank: train() must broadcast rank 0's
     np.random.seed(3)
     game = InflexionGame(7, max_turns=6, max_power=6)
     nnet = nnet_mod.NNetWrapper(game, device="cpu", infer_dtype=torch.float32)
