@@ -104,7 +104,8 @@ class Coach:
         evaluate, fused = self._evaluator()
         eng = SelfPlayEngine(per, int(self.args.numMCTSSims), evaluate, cpuct=self.args.cpuct,
                              temp_threshold=int(self.args.tempThreshold), seed=seed, max_turns=self.game._max_turns,
-                             game_id_base=game_id_base + rank * per, fused_head=fused)
+                             game_id_base=game_id_base + rank * per, fused_head=fused,
+                             nodes_per_game=dict(self.args).get("nodesPerGame", "auto"))
         if world > 1:                                   # every rank plays the full episode length (all-gather shapes agree)
             while eng.move < eng.max_moves:
                 eng.play_move()

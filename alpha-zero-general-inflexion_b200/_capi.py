@@ -25,7 +25,7 @@ class MctsConfig(C.Structure):
 
 class MctsLayout(C.Structure):
     _fields_ = [(n, c_int64) for n in ("rows", "q64", "node_key", "node_head", "hash", "free_stack", "per_game",
-                                        "path", "roots", "leaves", "total")]
+                                        "path", "roots", "leaves", "sym", "total")]
 
 
 # name -> (restype, argtypes); every symbol include/ifx_b200.h declares
@@ -70,7 +70,7 @@ PROTOTYPES = {
 
 ERRORS = {-1: "IFX_E_ARG (bad argument)", -2: "IFX_E_CUDA", -3: "IFX_E_NODEVICE"}
 FAULTS = {1: "node pool exhausted (raise nodes_per_game)", 2: "no valid action", 4: "search path deeper than max_depth",
-          8: "hash table full", 16: "invalid action"}
+          8: "hash table full", 16: "invalid action", 32: "visit count reached 2^17"}
 
 
 class IfxError(RuntimeError):

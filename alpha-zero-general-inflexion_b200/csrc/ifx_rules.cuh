@@ -32,8 +32,7 @@ IFX_HD int ifx_num_valid(const ifx_state& s) { return 6 * ifx_popc64(ifx_own(s))
 
 // execute_move, InflexionGame.py:273-310 (the action must be valid).  Updates s in place:
 // board, outcome (relative to the NEW side to move), turn+1, player flipped.
-IFX_HD void ifx_apply(ifx_state& s, int action) {
-  const int m = action / IFX_CELLS, cell = action - m * IFX_CELLS;
+IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) {     // m = move type 0..6, cell = r*7+q
   const uint64_t src = 1ull << cell;
   uint64_t own = ifx_own(s), opp = ifx_opp(s);
   uint64_t p0 = s.p0, p1 = s.p1, p2 = s.p2;
@@ -78,6 +77,11 @@ IFX_HD void ifx_apply(ifx_state& s, int action) {
   s.turn = (uint16_t)(s.turn + 1);
   s.player ^= 1;                                             // :310; the setter flips WON <-> LOST (Game.py:59-62)
   s.outcome = (uint8_t)(out == IFX_WON ? IFX_LOST : (out == IFX_LOST ? IFX_WON : out));
+}
+
+IFX_HD void ifx_apply(ifx_state& s, int action) {
+  const int m = action / IFX_CELLS;
+  ifx_apply_move(s, m, action - m * IFX_CELLS);
 }
 
 // Value of a terminal state as MCTS.py:87 reads it (GameOutcome.value, flags.py:32-36).

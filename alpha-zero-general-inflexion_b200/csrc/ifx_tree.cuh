@@ -16,7 +16,9 @@
 #include "ifx_rules.cuh"
 #include "ifx_philox.cuh"
 
-#define IFX_MAX_DEPTH 32           // one path level per lane
+#define IFX_PATH_CHUNK 32          // path levels held in registers at a time: one level per lane
+#define IFX_MAX_DEPTH 352          // longest search path accepted (a game has at most 344 plies: no real limit)
+#define IFX_NS_LIMIT (1 << 17)     // visit counts occupy 17 bits of an N word; the float32 sqrt identity holds below it
 
 struct alignas(16) IfxGame {       // 64 bytes per game
   int32_t sims_done;               // root-level search() calls finished in the current move (MCTS.py:45-46)
@@ -100,7 +102,6 @@ IFX_HD int ifx_compact_to_action(const ValidSet& V, int ci) {
   }
   return IFX_SPAWN * IFX_CELLS + ifx_nth_set_bit64(V.spawn, ci - spread);
 }
-
 // per-node header: Ns and the two square roots PUCT needs, refreshed whenever Ns changes (off the select path)
 struct alignas(16) IfxHead { int32_t ns; float sq_seen, sq_unseen; int32_t pad; };
 IFX_HD IfxHead ifx_head_of(int ns) {
@@ -122,10 +123,13 @@ struct TreeParams {
   IfxKey* hash;         // [G][H]
   uint16_t* free_stack; // [G][C]
   IfxGame* games;       // [G]
-  IfxU4* path;          // [G][32]   {slot << 9 | action, N word, Q bits, Ns} per level (valid while a leaf is pending)
+  IfxU4* path;          // [G][path_stride]  {slot << 9 | row entry, N word, Q bits, Ns} per level (valid while a leaf is
+                        // pending); levels beyond the 32 a warp holds in registers live only here
   ifx_state* roots;     // [G]
   ifx_state* leaves;    // [G]
-  int32_t G, C, H, maxd, num_sims, logits, term_budget;
+  uint8_t* sym;         // [G][sym_cap][64]  source cell of every destination cell under the random_symmetry of simulation i of
+                        // the CURRENT move (filled when the move starts); byte 63 of a row = the symmetry code
+  int32_t G, C, H, maxd, path_stride, sym_cap, num_sims, logits, term_budget;
   float dir_alpha, dir_eps;   // optional Dirichlet root noise (eps = 0: off = the reference's behaviour)
   uint64_t* debug;      // optional [G][8]: ns stamps {start, loads done, expanded, backed up, first level done, end}, depth, probes
   float cpuct;
@@ -148,7 +152,7 @@ IFX_HD TreeParams tree_rebase(const TreeParams& P, int g) {
   TreeParams L = P;
   L.rows += (int64_t)g * P.C * 3 * IFX_ROW; L.q64 += (int64_t)g * P.C * 344;
   L.node_key += (int64_t)g * P.C; L.node_head += (int64_t)g * P.C; L.hash += (int64_t)g * P.H;
-  L.free_stack += (int64_t)g * P.C; L.games += g; L.path += (int64_t)g * IFX_MAX_DEPTH; L.roots += g; L.leaves += g;
+  L.free_stack += (int64_t)g * P.C; L.games += g; L.path += (int64_t)g * P.path_stride; L.roots += g; L.leaves += g; L.sym += (int64_t)g * P.sym_cap * 64;
   return L;
 }
 
@@ -159,20 +163,6 @@ IFX_HD float* tree_row(const TreeParams& P, int g, int slot, int which) {
 IFX_HD bool tree_action_bit(uint64_t own, uint64_t spawn, int a) {
   const int m = a / IFX_CELLS, cell = a - m * IFX_CELLS;
   return ((m == IFX_SPAWN ? spawn : own) >> cell) & 1ull;
-}
-
-// validity of the four consecutive actions a .. a+3 (a % 4 == 0) as bits 0..3; planes are 49 cells long, so a
-// group can straddle two move types
-IFX_HD uint32_t tree_valid4(uint64_t own, uint64_t spawn, int a) {
-  if (a >= IFX_ACTIONS) return 0u;
-  const int m = a / IFX_CELLS, c = a - m * IFX_CELLS;
-  const uint64_t cur = m == IFX_SPAWN ? spawn : own;
-  uint32_t bits = (uint32_t)(cur >> c) & 0xFu;             // masks are 49 bits wide: cells beyond 48 read 0
-  if (c > IFX_CELLS - 4 && m < IFX_SPAWN) {                // the tail of the group belongs to move type m+1
-    const uint64_t nxt = (m + 1 == IFX_SPAWN) ? spawn : own;
-    bits |= ((uint32_t)nxt << (IFX_CELLS - c)) & 0xFu;
-  }
-  return bits;
 }
 
 // ---- hash (open addressing, linear probing, never deleted from: rebuilt when nodes are reclaimed) ----
@@ -216,7 +206,7 @@ IFX_D int tree_hash_resolve(const TreeParams& P, int g, uint64_t k0, uint64_t k1
 // copied into shared memory by the TMA engine right away (no registers held, the copy flies under the expansion),
 // the backup patches the one edge it changes, and every simulation of the wave selects from the mirror: one
 // HBM read of the root per wave and no dependent round trip at the start of a simulation.
-struct alignas(16) RootMirror { float rows[3 * IFX_ROW]; IfxHead head; IfxKey key; uint64_t mbar; uint64_t pad; };
+struct alignas(16) RootMirror { float rows[3 * IFX_ROW]; IfxHead head; IfxKey key; ifx_state root; uint64_t mbar; uint64_t pad; };
 
 #ifdef IFX_HOSTSIM
 static inline void ifx_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
@@ -244,12 +234,13 @@ IFX_D void tree_mirror_fetch(const TreeParams& P, int g, int slot, int nv, RootM
   for (int which = 0; which < 3; ++which) memcpy(M->rows + which * IFX_ROW, src + which * 4 * IFX_ROW, bytes);
   M->head = P.node_head[(int64_t)g * P.C + slot];
   M->key = P.node_key[(int64_t)g * P.C + slot];
+  M->root = P.roots[g];
 #else
   if (IFX_LANE0) {
     const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&M->mbar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(3u * bytes + 32u) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(3u * bytes + 32u + 64u) : "memory");
     if (bytes) {
       ifx_bulk_g2s(M->rows, src, bytes, &M->mbar);
       ifx_bulk_g2s(M->rows + IFX_ROW, src + 4 * IFX_ROW, bytes, &M->mbar);
@@ -257,6 +248,7 @@ IFX_D void tree_mirror_fetch(const TreeParams& P, int g, int slot, int nv, RootM
     }
     ifx_bulk_g2s(&M->head, &P.node_head[(int64_t)g * P.C + slot], 16u, &M->mbar);
     ifx_bulk_g2s(&M->key, &P.node_key[(int64_t)g * P.C + slot], 16u, &M->mbar);
+    ifx_bulk_g2s(&M->root, &P.roots[g], 64u, &M->mbar);    // the root position every simulation of the wave starts from
   }
 #endif
 }
@@ -285,6 +277,7 @@ IFX_D void tree_mirror_fetch_now(const TreeParams& P, int g, int slot, int nv, R
     }
     if (l == 0) ifx_cp_async16(&M->head, &P.node_head[(int64_t)g * P.C + slot]);
     if (l == 1) ifx_cp_async16(&M->key, &P.node_key[(int64_t)g * P.C + slot]);
+    if (l >= 4 && l < 8) ifx_cp_async16(reinterpret_cast<char*>(&M->root) + 16 * (l - 4), reinterpret_cast<const char*>(&P.roots[g]) + 16 * (l - 4));
   }
   ifx_cp_async_wait();
   IFX_SYNCWARP();
@@ -333,12 +326,14 @@ IFX_HD void tree_update_edge(const TreeParams& P, int g, int slot, int a, uint32
 // Back `v` (the value returned by the deepest search() call) up the first `depth` edges of the path; levels
 // are independent: distinct nodes (the turn strictly grows along a path).  `leaf_slot` is the node the last
 // edge leads to (-1: terminal state, no node).  Level 0 is the root: `mirror` (nullable) is kept in step.
-IFX_D void tree_backup_apply(const TreeParams& P, int g, int depth, const LaneVar<IfxU4>& path, double v, bool v_is32,
-                             int leaf_slot, RootMirror* mirror) {
+IFX_D uint32_t tree_backup_apply(const TreeParams& P, int g, int depth, const LaneVar<IfxU4>& path, double v, bool v_is32,
+                                 int leaf_slot, RootMirror* mirror) {
   LaneVar<uint32_t> edge, below;
+  LaneVar<int> ovf;
   IFX_FOR_LANES(l) { edge[l] = path[l].x; }
   lanes_shift_down(edge, below);                            // path entry one level deeper
   IFX_FOR_LANES(l) {
+    ovf[l] = 0;
     if (l < depth) {
       const int slot = (int)(edge[l] >> 9), a = (int)(edge[l] & 511u);
       const double vl = ((depth - 1 - l) & 1) ? -v : v;     // each level returns -v to its parent (MCTS.py:145)
@@ -348,9 +343,65 @@ IFX_D void tree_backup_apply(const TreeParams& P, int g, int depth, const LaneVa
       const IfxHead hd = ifx_head_of((int)path[l].w + 1);   // MCTS.py:144
       P.node_head[(int64_t)g * P.C + slot] = hd;
       if (mr) mr->head = hd;
+      ovf[l] = (int)path[l].w + 1 >= IFX_NS_LIMIT ? 1 : 0;  // N(s,a) <= Ns(s): one test guards the 17-bit count field too
     }
   }
   IFX_SYNCWARP();
+  return lanes_ballot(ovf);
+}
+
+// The same for a path longer than one register chunk (rare: > 32 edges): every chunk is read back from P.path, where
+// the descent left it (full chunks are spilled as they fill, the caller spills the last partial one).  Chunk 0 holds
+// the root edge (`mirror`).  Kept out of line so that the hot kernel's register allocation does not see it.
+IFX_D_NOINLINE uint32_t tree_backup_from_hbm(const TreeParams P, int g, int depth, double v, bool v_is32, int leaf_slot,
+                                             RootMirror* mirror) {
+  uint32_t ovf = 0;
+  IFX_SYNCWARP();
+  for (int base = 0; base < depth; base += IFX_PATH_CHUNK) {
+    const int n = depth - base < IFX_PATH_CHUNK ? depth - base : IFX_PATH_CHUNK;
+    LaneVar<IfxU4> pc;
+    IFX_FOR_LANES(l) {
+      IfxU4 e = {0u, 0u, 0u, 0u};
+      if (l < n) e = P.path[(int64_t)g * P.path_stride + base + l];
+      pc[l] = e;
+    }
+    const int next = base + IFX_PATH_CHUNK < depth ? (int)(P.path[(int64_t)g * P.path_stride + base + IFX_PATH_CHUNK].x >> 9) : leaf_slot;
+    const double vc = ((depth - base - n) & 1) ? -v : v;    // sign of level base+l: (depth-1-base-l) = (n-1-l) + (depth-base-n)
+    ovf |= tree_backup_apply(P, g, n, pc, vc, v_is32, next, base == 0 ? mirror : nullptr);
+  }
+  return ovf;
+}
+
+// Move type and cell of compact entry ci, found by the whole warp: lane l tests cells l and l+32 of the mask (is it
+// set, and is its rank k?), two ballots name the cell -- a dozen instructions with a short dependency chain instead of
+// an integer division and a six-step binary search on population counts.
+#ifdef IFX_HOSTSIM
+static inline float ifx_rcp_approx(float x) { return 1.0f / x; }
+#else
+IFX_D float ifx_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+IFX_D void tree_compact_to_move(const ValidSet& V, int ci, int* move_type, int* cell) {
+  const int spread = 6 * V.n_own;
+  int m = IFX_SPAWN, k = ci - spread;
+  uint64_t mask = V.spawn;
+  if (ci < spread) {
+    // ci / n_own for ci <= 293, n_own <= 49: (ci + 0.5) / n_own is at least 0.5/49 away from an integer, far more
+    // than the error of an approximate reciprocal
+    m = (int)(((float)ci + 0.5f) * ifx_rcp_approx((float)V.n_own));
+    k = ci - m * V.n_own;
+    mask = V.own;
+  }
+  const uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
+  const int plo = ifx_popc32(lo);
+  LaneVar<int> hit0, hit1;
+  IFX_FOR_LANES(l) {
+    const uint32_t below = (1u << l) - 1u;
+    hit0[l] = (((lo >> l) & 1u) && ifx_popc32(lo & below) == k) ? 1 : 0;
+    hit1[l] = (((hi >> l) & 1u) && plo + ifx_popc32(hi & below) == k) ? 1 : 0;
+  }
+  const uint32_t b0 = lanes_ballot(hit0), b1 = lanes_ballot(hit1);
+  *move_type = m;
+  *cell = b0 ? ifx_ffs32(b0) - 1 : 31 + ifx_ffs32(b1);
 }
 
 // ---- PUCT arg-max over the valid actions of one node (MCTS.py:114-129) ----
@@ -447,10 +498,15 @@ IFX_D float tree_pairwise_sum343(const float* buf) {
   return lanes_bcast(r, 0);
 }
 
-// policy row of the pending leaf, fetched ahead of use in the row layout (lane l: actions 4l+128j .. +3)
-struct PolicyRegs { LaneVar<IfxF4> p[3]; };
+// ---- the net's answer for the pending leaf, staged in shared memory ----
+// Per warp: `buf` (352 floats) receives the row the net wrote for this game -- float32 probabilities (exact mode), or
+// the binary16 head output (fused mode: 344 halfs in the lower half of buf; the upper half later holds the valid
+// logits in compact order) -- and `cells` two 64-byte lists: the node's own cells and its spawn cells in ascending
+// order, from which the action of any compact row entry follows in a few instructions.
+struct alignas(16) ExpandScratch { float buf[IFX_ROW]; uint8_t own_cell[64]; uint8_t spawn_cell[64]; };
 
-IFX_D void tree_policy_load(const float* pi, bool aligned, PolicyRegs& R) {
+// exact mode: pi row (float32, >= 343 entries) -> buf.  Issued with the first round trip.
+IFX_D void tree_stage_policy(const float* pi, bool aligned, float* buf) {
   IFX_FOR_LANES(l) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -464,125 +520,123 @@ IFX_D void tree_policy_load(const float* pi, bool aligned, PolicyRegs& R) {
         if (i + 2 < IFX_ACTIONS) v.z = pi[i + 2];
         if (i + 3 < IFX_ACTIONS) v.w = pi[i + 3];
       }
-      R.p[j][l] = v;
+      if (i < IFX_ROW) *reinterpret_cast<IfxF4*>(buf + i) = v;
+    }
+  }
+}
+// fused mode: binary16 head row (343 logits + the value pre-activation, 8-byte aligned) -> lower half of buf
+IFX_D void tree_stage_head(const uint16_t* head, float* buf) {
+  uint16_t* sh = reinterpret_cast<uint16_t*>(buf);
+  IFX_FOR_LANES(l) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      if (i < 344) *reinterpret_cast<uint2*>(sh + i) = *reinterpret_cast<const uint2*>(head + i);
     }
   }
 }
 
-// Fused head mode (policy_is_logits = 2): `head` is the net's last GEMM output for this game, binary16
-// [>= 344]: 343 policy logits + the value pre-activation.  The reference computes exp(log_softmax(logits))
-// (NNet.py:94 with InflexionNNet.py:54), masks it and renormalises over the valid moves (MCTS.py:95-97); the
-// softmax denominator cancels in that renormalisation, so this returns only e_i = exp(logit_i - max) and
-// tree_expand divides by the sum over the VALID moves.  Also returns tanh(value).  No elementwise kernel runs
-// between the GEMM and the tree.  (float32 throughout; agreement with the fp32 module is a tolerance, 1e-3.)
-IFX_D float tree_head_exp(const uint16_t* head, PolicyRegs& R) {
-  LaneVar<float> lmax;
-  IFX_FOR_LANES(l) {
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int i = 4 * l + 128 * j;
-      IfxF4 v = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (i < 344) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(head + i);        // four halfs, 8-byte aligned
-        v.x = ifx_h2f((uint16_t)(raw.x & 0xFFFFu)); v.y = ifx_h2f((uint16_t)(raw.x >> 16));
-        v.z = ifx_h2f((uint16_t)(raw.y & 0xFFFFu)); v.w = ifx_h2f((uint16_t)(raw.y >> 16));
-      }
-      R.p[j][l] = v;
-      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), v.z));
-      if (i + 3 < IFX_ACTIONS) mx = fmaxf(mx, v.w);                         // element 343 is the value, not a logit
-    }
-    lmax[l] = mx;
+// rank of `cell` among the set bits of a 49-bit mask given as two words
+IFX_HD int ifx_rank_lohi(uint32_t lo, uint32_t hi, int plo, int cell) {
+  return cell < 32 ? ifx_popc32(lo & ((1u << cell) - 1u)) : plo + ifx_popc32(hi & ((1u << (cell - 32)) - 1u));
+}
+
+// action of compact entry ci, from the cell lists (see ExpandScratch)
+IFX_D int tree_entry_action(const ExpandScratch* S, int ci, int n_own, int spread, float inv_n_own) {
+  if (ci < spread) {
+    const int m = (int)(((float)ci + 0.5f) * inv_n_own);    // ci / n_own, see tree_compact_to_move
+    return m * IFX_CELLS + (int)S->own_cell[ci - m * n_own];
   }
-  const float m = lanes_max_f32(lmax);
-  LaneVar<float> val;
-  IFX_FOR_LANES(l) {
-    val[l] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int i = 4 * l + 128 * j;
-      IfxF4 v = R.p[j][l];
-      if (i == 340) val[l] = ifx_tanhf(v.w);                                // lane 21, j = 2 holds element 343
-      // exp(x - m) = 2^((x - m) * log2(e)): one multiply-add and one MUFU.EX2 per prior
-      const float L2E = 1.4426950408889634f, mb = -m * L2E;
-      v.x = i < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.x, L2E, mb)) : 0.0f; v.y = i + 1 < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.y, L2E, mb)) : 0.0f;
-      v.z = i + 2 < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.z, L2E, mb)) : 0.0f; v.w = i + 3 < IFX_ACTIONS ? ifx_fast_exp2f(fmaf(v.w, L2E, mb)) : 0.0f;
-      R.p[j][l] = v;
-    }
-  }
-  return lanes_bcast(val, 21);
+  return IFX_SPAWN * IFX_CELLS + (int)S->spawn_cell[ci - spread];
 }
 
 // ---- expansion of the pending leaf (MCTS.py:89-112) ----
-// returns the slot, or -1 with a fault bit set; *leaf_nv = number of valid actions of the new node
-IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, const PolicyRegs& R, float* buf,
-                      const bool fused, int* leaf_nv) {
+// The work is laid out over the node's VALID actions (86 on average, three per lane), not over the 343 actions of the
+// net's row: the masked renormalisation (MCTS.py:95-97) needs an exp / a division / a store only for those.
+//   exact mode: policies *= valids happens in place in buf (invalid entries zeroed), policies.sum() is numpy's pairwise
+//     float32 sum over the dense vector, then one IEEE division per valid entry -- bit for bit the reference's numbers.
+//   fused mode: the reference computes exp(log_softmax(logits)) (NNet.py:94 with InflexionNNet.py:54), masks and
+//     renormalises; the softmax denominator cancels in that renormalisation, so e_i = exp(logit_i - max over the valid
+//     logits) / sum over the valid e_i is the same number (float32 tolerance; one MUFU.EX2 per prior).
+// returns the slot, or -1 with a fault bit set; *leaf_nv = number of valid actions of the new node; *leaf_v (fused
+// mode only) = tanh of the value pre-activation
+IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& leaf, ExpandScratch* S, const bool fused,
+                      int* leaf_nv, float* leaf_v) {
   const ValidSet V = ifx_valid_set(ifx_own(leaf), ifx_spawn_mask(leaf));
   *leaf_nv = V.nv;
-  LaneVar<uint32_t> vbits;                                  // validity of the lane's 12 actions (4 bits per group)
-  LaneVar<IfxF4> m0, m1, m2;                                // policies *= valids (MCTS.py:95)
+  float* buf = S->buf;
+  const uint32_t olo = (uint32_t)V.own, ohi = (uint32_t)(V.own >> 32), slo = (uint32_t)V.spawn, shi = (uint32_t)(V.spawn >> 32);
+  const int oplo = ifx_popc32(olo), splo = ifx_popc32(slo);
+  const int spread = 6 * V.n_own;
+  // pop the slot for the NEXT expansion now: the load flies under the whole expansion (its value is used last)
+  int next = -1;
+  if (G.free_top > 0) next = (int)P.free_stack[(int64_t)g * P.C + (G.free_top - 1)];
+  IFX_SYNCWARP();                                           // the staged row (written by other lanes) is complete
+  // cell lists, and (exact mode) policies *= valids in place (MCTS.py:95)
   IFX_FOR_LANES(l) {
-    uint32_t vb = 0;
-    IfxF4 mv[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int i = 4 * l + 128 * j;
-      const uint32_t b = tree_valid4(V.own, V.spawn, i);
-      vb |= b << (4 * j);
-      IfxF4 v = R.p[j][l];
-      v.x = (b & 1u) ? v.x : 0.0f; v.y = (b & 2u) ? v.y : 0.0f;
-      v.z = (b & 4u) ? v.z : 0.0f; v.w = (b & 8u) ? v.w : 0.0f;
-      mv[j] = v;
-      if (!fused && i < IFX_ROW) *reinterpret_cast<IfxF4*>(buf + i) = v;
+    for (int half = 0; half < 2; ++half) {
+      const int c = l + 32 * half;
+      if (c < IFX_CELLS) {
+        const bool ownb = (V.own >> c) & 1ull, spb = (V.spawn >> c) & 1ull;
+        if (ownb) S->own_cell[ifx_rank_lohi(olo, ohi, oplo, c)] = (uint8_t)c;
+        if (spb) S->spawn_cell[ifx_rank_lohi(slo, shi, splo, c)] = (uint8_t)c;
+        if (!fused) {
+          if (!ownb) {
+#pragma unroll
+            for (int m = 0; m < IFX_SPAWN; ++m) buf[m * IFX_CELLS + c] = 0.0f;
+          }
+          if (!spb) buf[IFX_SPAWN * IFX_CELLS + c] = 0.0f;
+        }
+      }
     }
-    vbits[l] = vb; m0[l] = mv[0]; m1[l] = mv[1]; m2[l] = mv[2];
   }
-  float total;
-  if (fused) {                                              // float32 net output: any summation order is within tolerance
+  IFX_SYNCWARP();
+  const float inv_n_own = V.n_own > 0 ? ifx_rcp_approx((float)V.n_own) : 0.0f;
+  float total, scale = 0.0f, mb = 0.0f;
+  const float L2E = 1.4426950408889634f;
+  uint16_t* sh = reinterpret_cast<uint16_t*>(buf);          // fused: staged halfs [0,344), compact valid logits [352, 352+nv)
+  if (fused) {
+    *leaf_v = ifx_tanhf(ifx_h2f(sh[IFX_ACTIONS]));
+    LaneVar<float> lmax;
+    IFX_FOR_LANES(l) {
+      float mx = -INFINITY;
+      for (int ci = l; ci < V.nv; ci += 32) {
+        const uint16_t hx = sh[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)];
+        sh[IFX_ROW + ci] = hx;
+        mx = fmaxf(mx, ifx_h2f(hx));
+      }
+      lmax[l] = mx;
+    }
+    const float m = lanes_max_f32(lmax);
+    mb = -m * L2E;
     LaneVar<float> part;
     IFX_FOR_LANES(l) {
-      part[l] = ((m0[l].x + m0[l].y) + (m0[l].z + m0[l].w)) + ((m1[l].x + m1[l].y) + (m1[l].z + m1[l].w)) +
-                ((m2[l].x + m2[l].y) + (m2[l].z + m2[l].w));
+      float acc = 0.0f;                                     // exp(x - m) = 2^((x - m) * log2(e)): one multiply-add and one MUFU.EX2
+      for (int ci = l; ci < V.nv; ci += 32) acc += ifx_fast_exp2f(fmaf(ifx_h2f(sh[IFX_ROW + ci]), L2E, mb));
+      part[l] = acc;
     }
-    total = lanes_sum_f32(part);
+    total = lanes_sum_f32(part);                            // float32 net output: any summation order is within tolerance
   } else {
-    IFX_SYNCWARP();
     total = tree_pairwise_sum343(buf);                      // policies.sum() over the DENSE vector, numpy's order
   }
   const bool uniform = !(total > 0.0f);                     // MCTS.py:98-107: all valid moves masked
   if (uniform) total = (float)V.nv;                         // sum of 0/1 values is exact in any order
-  const float inv_total = fused ? ifx_frcp(total) : 0.0f;
+  if (fused) scale = ifx_frcp(total);
   const int slot = G.next_slot;
   if (slot < 0) { G.faults |= IFX_F_POOL; return -1; }
   if (G.leaf_hpos < 0) { G.faults |= IFX_F_HASH; return -1; }
-  // pop the slot for the NEXT expansion now; the load is off the critical path
-  int next = -1;
-  if (G.free_top > 0) next = (int)P.free_stack[(int64_t)g * P.C + (G.free_top - 1)];
   float* prow = tree_row(P, g, slot, 0);
   float* nrow = tree_row(P, g, slot, 1);
   IFX_FOR_LANES(l) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int i = 4 * l + 128 * j;
-      const uint32_t b = (vbits[l] >> (4 * j)) & 0xFu;
-      if (i < IFX_ACTIONS && b) {                           // (divergent only across lanes with no valid action in the group)
-        IfxF4 v = j == 0 ? m0[l] : (j == 1 ? m1[l] : m2[l]);
-        if (uniform) { v.x = v.y = v.z = v.w = 1.0f; }       // policies = valids (MCTS.py:105)
-        if (fused) {                                        // one reciprocal, then multiplies
-          v.x *= inv_total; v.y *= inv_total; v.z *= inv_total; v.w *= inv_total;
-        } else {
-          // policies /= sum.  A dummy 1.0 for the invalid entries of the group keeps zero numerators out of the
-          // IEEE division's slow path (which the whole warp would otherwise take).
-          v.x = ifx_fdiv((b & 1u) ? v.x : 1.0f, total); v.y = ifx_fdiv((b & 2u) ? v.y : 1.0f, total);
-          v.z = ifx_fdiv((b & 4u) ? v.z : 1.0f, total); v.w = ifx_fdiv((b & 8u) ? v.w : 1.0f, total);
-        }
-        // compact position of a valid action = number of valid actions below it
-        int c = ifx_valid_below(V, i);
-        if (b & 1u) { prow[c] = v.x; c += 1; }
-        if (b & 2u) { prow[c] = v.y; c += 1; }
-        if (b & 4u) { prow[c] = v.z; c += 1; }
-        if (b & 8u) { prow[c] = v.w; }
+    for (int ci = l; ci < V.nv; ci += 32) {                 // coalesced: consecutive lanes, consecutive row entries
+      float p;
+      if (fused) {
+        p = uniform ? scale : ifx_fast_exp2f(fmaf(ifx_h2f(sh[IFX_ROW + ci]), L2E, mb)) * scale;
+      } else {                                              // policies /= sum (policies = valids in the fallback, MCTS.py:105)
+        p = ifx_fdiv(uniform ? 1.0f : buf[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)], total);
       }
+      prow[ci] = p;
     }
     const IfxU4 z = {IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH};   // Nsa = 0 for every valid action
     for (int c4 = 4 * l; c4 < V.nv; c4 += 128) *reinterpret_cast<IfxU4*>(nrow + c4) = z;
@@ -644,28 +698,45 @@ IFX_D void tree_root_noise(const TreeParams& P, int g, const IfxGame& G, int slo
   tree_root_noise_apply(tree_row(P, g, slot, 0), P.seed, G.game_id, (uint32_t)G.move_idx, nv, P.dir_alpha, P.dir_eps);
 }
 
-// random_symmetry of (game, move, sim): k + 6*shift + 42*axis (InflexionGame.py:115-122; MCTS.py:90-92)
-IFX_D int tree_draw_symmetry(const TreeParams& P, const IfxGame& G) {
-  const IfxRand4 r = ifx_philox(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)G.sims_done, IFX_RNG_SYMMETRY);
+// random_symmetry of (game, move, sim): k + 6*shift + 42*axis (InflexionGame.py:115-122; MCTS.py:90-92).
+// The draw is a pure function of (seed; game, move, sim) -- ~100 lane-uniform instructions of Philox -- and what a leaf
+// needs from it is the source cell of each of the 49 destination cells.  Both are computed for a whole move when the
+// move starts (tree_begin_move; 32 simulations at a time across the lanes) into a 64-byte row per simulation, so a
+// simulation issues two byte loads at an address it knows from its first instruction and nothing depends on them
+// until (if) it ends on a new leaf.  Simulations beyond the table (num_sims raised past sym_cap by set_params) draw
+// inline.
+IFX_HD int tree_symmetry_code(uint64_t seed, uint32_t game, uint32_t move, uint32_t sim) {
+  const IfxRand4 r = ifx_philox(seed, game, move, sim, IFX_RNG_SYMMETRY);
   return (int)(r.w[0] % 6u) + 6 * (int)(r.w[1] % 7u) + 42 * (int)(r.w[2] % 3u);
 }
 
 // Source cell of every (symmetry, destination cell): 126 x 64 bytes, filled once per process by
-// tree_sym_lut_kernel (ifx_mcts_create).  Two coalesced byte loads per lane replace ~130 instructions of index
-// arithmetic per leaf; the loads are issued as soon as the symmetry is drawn, i.e. under the hash probe.
+// tree_sym_lut_kernel (ifx_mcts_create).
+struct SymSrc { LaneVar<int> a, b; };                        // lane l: source cells of destination cells l and l + 32
 #ifdef IFX_HOSTSIM
-struct SymSrc { LaneVar<int> a, b; };
-static inline void tree_sym_src_issue(int sym, SymSrc& S) {
-  for (int l = 0; l < 32; ++l) { S.a[l] = ifx_sym_src(sym, l); S.b[l] = l + 32 < IFX_CELLS ? ifx_sym_src(sym, l + 32) : 0; }
-}
+static inline int tree_sym_lut(int sym, int cell) { return cell < IFX_CELLS ? ifx_sym_src(sym, cell) : 0; }
 #else
 __device__ uint8_t g_ifx_sym_lut[126 * 64];
-struct SymSrc { LaneVar<int> a, b; };
-IFX_D void tree_sym_src_issue(int sym, SymSrc& S) {
-  const uint8_t* row = g_ifx_sym_lut + sym * 64 + (threadIdx.x & 31u);
-  S.a.v = row[0]; S.b.v = row[32];
-}
+IFX_D int tree_sym_lut(int sym, int cell) { return (int)g_ifx_sym_lut[sym * 64 + cell]; }
 #endif
+IFX_D_NOINLINE int tree_symmetry_code_slow(uint64_t seed, uint32_t game, uint32_t move, uint32_t sim) {
+  return tree_symmetry_code(seed, game, move, sim);
+}
+IFX_D void tree_fill_symmetries(const TreeParams& P, int g, uint32_t game, uint32_t move) {
+  uint8_t* tab = P.sym + (int64_t)g * P.sym_cap * 64;
+  for (int base = 0; base < P.sym_cap; base += 32) {
+    LaneVar<int> code;
+    IFX_FOR_LANES(l) { code[l] = tree_symmetry_code(P.seed, game, move, (uint32_t)(base + l)); }
+    for (int j = 0; j < 32; ++j) {
+      const int sym = lanes_bcast(code, j);
+      IFX_FOR_LANES(l) {
+        uint8_t* row = tab + (int64_t)(base + j) * 64;
+        row[l] = (uint8_t)tree_sym_lut(sym, l);
+        row[l + 32] = l + 32 == 63 ? (uint8_t)sym : (uint8_t)tree_sym_lut(sym, l + 32);
+      }
+    }
+  }
+}
 
 // planes of `st` under the symmetry whose source cells are S -> float32 [4][49] (the net's input row of this game)
 IFX_D void tree_write_nn_input(const ifx_state& st, const SymSrc& S, float* out) {
@@ -694,7 +765,7 @@ IFX_D uint64_t ifx_now_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltime
 
 template <bool DBG>
 IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int64_t pi_stride, const float* nn_v,
-                          float* nn_in, float* buf, RootMirror* mirror) {
+                          float* nn_in, ExpandScratch* scratch, RootMirror* mirror) {
   const TreeParams P = tree_rebase(P0, g0);
   const int g = 0;
   nn_in += (int64_t)g0 * 196;
@@ -709,31 +780,30 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
   int mirror_slot = G.root_slot;
   if (mirror_slot >= 0) tree_mirror_fetch(P, g, mirror_slot, G.root_nv, mirror);
   const ifx_state leaf = P.leaves[g];
-  float leaf_v;
-  PolicyRegs pol;
-  if (P.logits == 2) {                                      // binary16 head output: exp + tanh fused here
-    leaf_v = tree_head_exp(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g0 * pi_stride, pol);
+  float leaf_v = 0.0f;
+  if (P.logits == 2) {                                      // binary16 head output: exp + tanh are fused into the expansion
+    tree_stage_head(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g0 * pi_stride, scratch->buf);
   } else {
     leaf_v = nn_v[g0];
     const float* pi_row = nn_pi + (int64_t)g0 * pi_stride;
-    tree_policy_load(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, pol);
+    tree_stage_policy(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, scratch->buf);
   }
   LaneVar<IfxU4> path;
   // the first 8 levels of the pending leaf's path travel with the first round trip (one 128-byte line); deeper
   // paths (rare) fetch the rest once the record says so
   IFX_FOR_LANES(l) {
     IfxU4 e = {0u, 0u, 0u, 0u};
-    if (l < 8) e = P.path[(int64_t)g * IFX_MAX_DEPTH + l];
+    if (l < 8) e = P.path[(int64_t)g * P.path_stride + l];
     path[l] = e;
   }
   if (G.pending && G.path_len > 8) {
-    IFX_FOR_LANES(l) { if (l >= 8) path[l] = P.path[(int64_t)g * IFX_MAX_DEPTH + l]; }
+    IFX_FOR_LANES(l) { if (l >= 8) path[l] = P.path[(int64_t)g * P.path_stride + l]; }
   }
   if (G.faults) { if (mirror_slot >= 0) tree_mirror_wait(mirror); return; }
   if (DBG) dbg_t1 = ifx_now_ns() + (uint64_t)(G.pending & 0) + (uint64_t)(leaf.turn & 0);
   if (G.pending) {
     int leaf_nv = 0;
-    const int slot = tree_expand(P, g, G, leaf, pol, buf, P.logits == 2, &leaf_nv);
+    const int slot = tree_expand(P, g, G, leaf, scratch, P.logits == 2, &leaf_nv, &leaf_v);
     if (DBG) dbg_t2 = ifx_now_ns();
     if (mirror_slot >= 0) tree_mirror_wait(mirror);         // the backup patches the mirror: it must have landed
     if (slot >= 0) {
@@ -744,7 +814,10 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
         if (P.dir_eps > 0.0f) G.noise_due = 1;
       }
       // search() of the leaf returns -v, v a float32 (MCTS.py:112; NNet.py:94)
-      tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot, mirror_slot >= 0 ? mirror : nullptr);
+      const uint32_t ovf = G.path_len <= IFX_PATH_CHUNK
+          ? tree_backup_apply(P, g, G.path_len, path, -(double)leaf_v, true, slot, mirror_slot >= 0 ? mirror : nullptr)
+          : tree_backup_from_hbm(P, g, G.path_len, -(double)leaf_v, true, slot, mirror_slot >= 0 ? mirror : nullptr);
+      if (ovf) G.faults |= IFX_F_COUNT;
       G.sims_done += 1; G.n_sims += 1;
     }
     G.pending = 0;
@@ -754,8 +827,19 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
   }
   int term_left = P.term_budget > 0 ? P.term_budget : 0x7fffffff;
   while (!G.faults && G.sims_done < P.num_sims && term_left > 0 && !G.noise_due) {
-    ifx_state st = P.roots[g];                              // re-read per simulation (an L1/L2 hit) instead of sixteen
-    int depth = 0;                                          // registers held across the whole wave
+    // the root position: from the mirror (shared memory; it came with the root's rows) -- no round trip at the start
+    // of a simulation; straight from the workspace only while the root is not expanded yet (first wave of a move)
+    ifx_state st = mirror_slot >= 0 ? mirror->root : P.roots[g];
+    int depth = 0;
+    // this simulation's random_symmetry (source cells of the lane's two destination cells): requested now, used when
+    // (if) the simulation ends on a new leaf
+    SymSrc sym_src;
+    if (G.sims_done < P.sym_cap) {
+      IFX_FOR_LANES(l) { sym_src.a[l] = (int)P.sym[G.sims_done * 64 + l]; sym_src.b[l] = (int)P.sym[G.sims_done * 64 + l + 32]; }
+    } else {
+      const int sym = tree_symmetry_code_slow(P.seed, G.game_id, (uint32_t)G.move_idx, (uint32_t)G.sims_done);
+      IFX_FOR_LANES(l) { sym_src.a[l] = tree_sym_lut(sym, l); sym_src.b[l] = tree_sym_lut(sym, l + 32); }
+    }
     int slot = G.root_slot;                                 // -1: the root is not expanded yet
     bool verified = slot >= 0;                              // the cached root slot needs no key check
     RowRegs rows;
@@ -769,7 +853,15 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     }
     for (;;) {
       if (st.outcome != IFX_ONGOING) {                      // MCTS.py:85-87: terminal, value is a Python number
-        tree_backup_apply(P, g, depth, path, -ifx_outcome_value(st.outcome), false, -1, mirror_slot >= 0 ? mirror : nullptr);
+        uint32_t ovf;
+        if (depth <= IFX_PATH_CHUNK) {
+          ovf = tree_backup_apply(P, g, depth, path, -ifx_outcome_value(st.outcome), false, -1, mirror_slot >= 0 ? mirror : nullptr);
+        } else {                                            // deep path: the last partial chunk joins the others in P.path
+          const int base = depth & ~(IFX_PATH_CHUNK - 1);
+          IFX_FOR_LANES(l) { if (base + l < depth) P.path[(int64_t)g * P.path_stride + base + l] = path[l]; }
+          ovf = tree_backup_from_hbm(P, g, depth, -ifx_outcome_value(st.outcome), false, -1, mirror_slot >= 0 ? mirror : nullptr);
+        }
+        if (ovf) G.faults |= IFX_F_COUNT;
         G.sims_done += 1; G.n_sims += 1; G.n_term += 1;
         term_left -= 1;
         break;
@@ -780,22 +872,24 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
       // whether the hint was right (the reference looks nodes up by planes, not by edge: SURVEY.md H1)
       if (inflight && !verified && !(rows.key.k0 == k0 && rows.key.k1 == k1)) slot = -1;
       if (slot < 0) {
-        // look the state up by key; the symmetry this simulation would feed the net with is drawn (Philox, ~100
-        // instructions) while the probe is in flight
+        // Look the state up by key.  Without a verified hint the probe almost always misses (the state is new), so the
+        // leaf is written out WHILE the probe is in flight: its planes under this simulation's symmetry to nn_in, the
+        // state and the path to the workspace.  If the probe hits after all (a transposition) the descent simply goes
+        // on; what was written is overwritten by the leaf this simulation ends on, or never read.
         const uint32_t h = ifx_hash_key(k0, k1);
         LaneVar<IfxKey> first;
         tree_hash_issue(P, g, h, first);
-        const int sym = tree_draw_symmetry(P, G);
-        SymSrc sym_src;
-        tree_sym_src_issue(sym, sym_src);
+        if (IFX_LANE0) P.leaves[g] = st;
+        {                                                   // the chunk in registers (earlier, full chunks are there already)
+          const int base = depth & ~(IFX_PATH_CHUNK - 1);
+          IFX_FOR_LANES(l) { if (base + l < depth) P.path[(int64_t)g * P.path_stride + base + l] = path[l]; }
+        }
+        tree_write_nn_input(st, sym_src, nn_in);
         slot = tree_hash_resolve(P, g, k0, k1, h, first, &miss_pos);
         if (DBG) dbg_probes += 1;
         if (slot >= 0) {
           tree_rows_load(P, g, slot, rows);
         } else {                                            // MCTS.py:89: leaf -> wait for the net
-          if (IFX_LANE0) P.leaves[g] = st;
-          IFX_FOR_LANES(l) { if (l < depth) P.path[(int64_t)g * IFX_MAX_DEPTH + l] = path[l]; }
-          tree_write_nn_input(st, sym_src, nn_in);
           G.path_len = (int16_t)depth; G.pending = 1; G.leaf_hpos = miss_pos;
           break;
         }
@@ -807,23 +901,29 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
       const int ci = tree_select(P, rows, at_root ? mirror->rows : tree_row(P, g, slot, 0), V.nv, &raw, &qsel);
       if (ci < 0) { G.faults |= IFX_F_NOVALID; break; }
       if (depth >= P.maxd) { G.faults |= IFX_F_DEPTH; break; }
-      IFX_FOR_LANES(l) {
-        if (l == depth) {
-          IfxU4 e; e.x = ((uint32_t)slot << 9) | (uint32_t)ci; e.y = raw; e.z = ifx_f2u(qsel); e.w = (uint32_t)rows.head.ns;
-          path[l] = e;
-        }
-      }
-      const int a = ifx_compact_to_action(V, ci);
-      depth += 1;
-      if (DBG && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
-      if (DBG) dbg_depth = depth > dbg_depth ? depth : dbg_depth;
-      // request the hinted child's rows BEFORE stepping the board: the loads fly while the rules run
+      // request the hinted child's rows FIRST -- the hint came out of the arg-max with the edge -- so that the loads
+      // fly under everything that follows: the path record, the entry -> move conversion and the rules step
+      const uint32_t edge_word = ((uint32_t)slot << 9) | (uint32_t)ci, node_ns = (uint32_t)rows.head.ns;
       const uint32_t hint = (raw >> IFX_N_HINT_SHIFT) & IFX_N_HINT_NONE;
       slot = (hint != IFX_N_HINT_NONE && (int)hint < P.C) ? (int)hint : -1;
       verified = false;
       inflight = slot >= 0;
       if (inflight) tree_rows_load(P, g, slot, rows);
-      ifx_apply(st, a);                                     // MCTS.py:132
+      IFX_FOR_LANES(l) {
+        if (l == (depth & (IFX_PATH_CHUNK - 1))) {
+          IfxU4 e; e.x = edge_word; e.y = raw; e.z = ifx_f2u(qsel); e.w = node_ns;
+          path[l] = e;
+        }
+      }
+      int mv_type, mv_cell;
+      tree_compact_to_move(V, ci, &mv_type, &mv_cell);
+      depth += 1;
+      if ((depth & (IFX_PATH_CHUNK - 1)) == 0) {            // a full chunk of 32 levels moves to P.path (rare)
+        IFX_FOR_LANES(l) { P.path[(int64_t)g * P.path_stride + depth - IFX_PATH_CHUNK + l] = path[l]; }
+      }
+      if (DBG && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
+      if (DBG) dbg_depth = depth > dbg_depth ? depth : dbg_depth;
+      ifx_apply_move(st, mv_type, mv_cell);                 // MCTS.py:132
     }
     if (G.pending) break;
   }
@@ -918,6 +1018,7 @@ IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
   G.noise_due = 0;
   G.leaf_hpos = -1;
   G.sims_done = root.outcome == IFX_ONGOING ? 0 : P.num_sims;   // a finished game is never searched
+  if (root.outcome == IFX_ONGOING) tree_fill_symmetries(P, g, G.game_id, (uint32_t)G.move_idx);
   if (root.outcome == IFX_ONGOING) tree_root_noise(P, g, G, root_slot, G.root_nv);   // (no-op unless dirichlet_eps > 0)
   if (IFX_LANE0) P.games[g] = G;
 }

@@ -20,13 +20,15 @@ struct ifx_mcts {
 };
 
 static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+static int32_t sym_cap_of(int32_t num_sims) { const int32_t n = num_sims > 128 ? num_sims : 128; return (n + 31) / 32 * 32; }
+static int32_t path_stride_of(int32_t max_depth) { return (max_depth + IFX_PATH_CHUNK - 1) / IFX_PATH_CHUNK * IFX_PATH_CHUNK; }
 
 static int check_cfg(const ifx_mcts_config* c) {
   if (!c) return IFX_E_ARG;
   if (c->n_games <= 0 || c->nodes_per_game < 32 || c->nodes_per_game > 16383) return IFX_E_ARG;
   if (c->hash_per_game < 64 || (c->hash_per_game & (c->hash_per_game - 1))) return IFX_E_ARG;
   if (c->hash_per_game < 2 * c->nodes_per_game) return IFX_E_ARG;
-  if (c->max_depth < 1 || c->max_depth > IFX_MAX_DEPTH || c->num_sims < 0) return IFX_E_ARG;
+  if (c->max_depth < 1 || c->max_depth > IFX_MAX_DEPTH || c->num_sims < 0 || c->num_sims >= IFX_NS_LIMIT) return IFX_E_ARG;
   if (c->policy_is_logits != 0 && c->policy_is_logits != 2) return IFX_E_ARG;
   if (c->terminal_sims_per_wave < 0) return IFX_E_ARG;
   if (c->dirichlet_eps < 0.0f || c->dirichlet_eps > 1.0f || (c->dirichlet_eps > 0.0f && !(c->dirichlet_alpha > 0.0f))) return IFX_E_ARG;
@@ -150,10 +152,10 @@ template <bool DBG>
 __global__ void __launch_bounds__(TREE_BLOCK, IFX_WAVE_MIN_BLOCKS)
 tree_wave_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_stride, const float* __restrict__ nn_v,
                  float* __restrict__ nn_in) {
-  __shared__ float buf[TREE_WARPS][IFX_ROW];
+  __shared__ ExpandScratch scratch[TREE_WARPS];
   __shared__ RootMirror mirror[TREE_WARPS];
   const int w = threadIdx.x >> 5, g = blockIdx.x * TREE_WARPS + w;
-  if (g < P.G) tree_wave_game<DBG>(P, g, nn_pi, pi_stride, nn_v, nn_in, buf[w], &mirror[w]);
+  if (g < P.G) tree_wave_game<DBG>(P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch[w], &mirror[w]);
 }
 
 __global__ void __launch_bounds__(TREE_BLOCK)
@@ -236,9 +238,10 @@ int ifx_mcts_get_layout(const ifx_mcts_config* c, ifx_mcts_layout* L) {
   L->hash = off;       off = align256(off + G * H * 16);
   L->free_stack = off; off = align256(off + G * C * 2);
   L->per_game = off;   off = align256(off + G * (int64_t)sizeof(IfxGame));
-  L->path = off;       off = align256(off + G * IFX_MAX_DEPTH * 16);
+  L->path = off;       off = align256(off + G * (int64_t)path_stride_of(c->max_depth) * 16);
   L->roots = off;      off = align256(off + G * (int64_t)sizeof(ifx_state));
   L->leaves = off;     off = align256(off + G * (int64_t)sizeof(ifx_state));
+  L->sym = off;        off = align256(off + G * (int64_t)sym_cap_of(c->num_sims) * 64);
   L->total = off;
   return IFX_OK;
 }
@@ -261,7 +264,9 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   P.node_head = (IfxHead*)(b + L.node_head); P.hash = (IfxKey*)(b + L.hash);
   P.free_stack = (uint16_t*)(b + L.free_stack); P.games = (IfxGame*)(b + L.per_game);
   P.path = (IfxU4*)(b + L.path); P.roots = (ifx_state*)(b + L.roots); P.leaves = (ifx_state*)(b + L.leaves);
+  P.sym = (uint8_t*)(b + L.sym); P.sym_cap = sym_cap_of(c->num_sims);
   P.G = c->n_games; P.C = c->nodes_per_game; P.H = c->hash_per_game; P.maxd = c->max_depth;
+  P.path_stride = path_stride_of(c->max_depth);
   P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.term_budget = c->terminal_sims_per_wave;
   P.dir_alpha = c->dirichlet_alpha; P.dir_eps = c->dirichlet_eps; P.cpuct = c->cpuct; P.seed = c->seed;
   P.debug = nullptr;
@@ -309,7 +314,7 @@ int ifx_mcts_wave_time(ifx_mcts* m, double* total_ms, int32_t* launches) {
 }
 
 int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct) {
-  if (!m || num_sims < 0) return IFX_E_ARG;
+  if (!m || num_sims < 0 || num_sims >= IFX_NS_LIMIT) return IFX_E_ARG;
   m->P.num_sims = m->cfg.num_sims = num_sims;
   m->P.cpuct = m->cfg.cpuct = cpuct;
   return IFX_OK;
@@ -349,9 +354,9 @@ int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const floa
     if (pi_stride < 344 || (pi_stride & 3) || ((uintptr_t)nn_pi & 7)) return IFX_E_ARG;
   } else if (!nn_v) return IFX_E_ARG;
 #ifdef IFX_HOSTSIM
-  float buf[IFX_ROW];
+  static ExpandScratch scratch;
   static RootMirror mirror;
-  for (int g = 0; g < m->P.G; ++g) tree_wave_game<false>(m->P, g, nn_pi, pi_stride, nn_v, nn_in, buf, &mirror);
+  for (int g = 0; g < m->P.G; ++g) tree_wave_game<false>(m->P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch, &mirror);
   if (m->P.dir_eps > 0.0f) for (int g = 0; g < m->P.G; ++g) body_root_noise(m->P, g);
   return ifx_after_launch();
 #else

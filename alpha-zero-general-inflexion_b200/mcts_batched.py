@@ -29,9 +29,27 @@ def default_pool_size(num_sims: int) -> int:
     return min(n, 16383)
 
 
+NODE_BYTES = 3 * 352 * 4 + 344 * 8 + 16 + 16 + 2 + 2 * 2 * 16      # rows + q64 + key + head + free-stack entry + hash share
+
+
+def auto_pool_size(n_games: int, num_sims: int, device, fraction: float = 0.5) -> int:
+    """Nodes per game for ``nodes_per_game="auto"``: as many as ``fraction`` of the device's FREE memory holds, between
+    ``default_pool_size`` and the format's limit of 16383.  The reference never frees a node; here a node is reclaimed
+    once the root's turn has passed its own (the only reclamation that cannot change a result: an unreachable-looking
+    node with a later turn can still be found again through a transposition).  A confident net keeps its principal
+    variation -- about ``num_sims`` new nodes per move -- alive for as many moves as the variation is deep, so the live
+    set can reach tens of times ``num_sims``; small batches (Coach, Arena, one-game MCTS objects) can afford that."""
+    floor = default_pool_size(num_sims)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return floor
+    free, _ = torch.cuda.mem_get_info(dev)
+    return int(max(floor, min(16383, fraction * free / (max(n_games, 1) * NODE_BYTES))))
+
+
 class BatchedMCTS:
-    def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | None = None,
-                 max_depth: int = 32, backend: Backend | None = None, fused_head: bool = False,
+    def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | str | None = None,
+                 max_depth: int = 352, backend: Backend | None = None, fused_head: bool = False,
                  pad_policy_rows: bool = True, terminal_sims_per_wave: int = 1, dirichlet_alpha: float = 0.0,
                  dirichlet_eps: float = 0.0):
         """fused_head: the net hands over its last GEMM output (float16 [G,344]: 343 policy logits + the value
@@ -42,6 +60,8 @@ class BatchedMCTS:
         per move.  The reference's MCTS has none, so the default (eps = 0) is off and the bit-exact parity holds."""
         self.be = backend or default_backend()
         self.n_games, self.num_sims = int(n_games), int(num_sims)
+        if nodes_per_game == "auto":
+            nodes_per_game = auto_pool_size(self.n_games, num_sims, self.be.device)
         nodes = int(nodes_per_game or default_pool_size(num_sims))
         hash_slots = 64
         while hash_slots < 2 * nodes:

@@ -37,6 +37,7 @@ extern "C" {
 #define IFX_F_DEPTH 4    /* search path deeper than max_depth                                    */
 #define IFX_F_HASH 8     /* hash table full                                                      */
 #define IFX_F_BADACTION 16 /* advance/step called with an action that is not valid               */
+#define IFX_F_COUNT 32   /* a node's visit count reached 2^17 (the width of the count field)     */
 
 /* ---- outcome codes, relative to the side to move (flags.py:32-44, Game.py:64-72) ------------- */
 #define IFX_ONGOING 0
@@ -124,8 +125,10 @@ typedef struct ifx_mcts_config {
   int32_t n_games;          /* concurrent game trees on this GPU                                  */
   int32_t nodes_per_game;   /* node pool capacity per game (<= 16383)                             */
   int32_t hash_per_game;    /* hash slots per game, power of two, >= 2*nodes_per_game             */
-  int32_t max_depth;        /* longest search path kept (<= 32: one level per lane)               */
-  int32_t num_sims;         /* args.numMCTSSims (MCTS.py:45)                                      */
+  int32_t max_depth;        /* longest search path accepted, 1..352 (a game has at most 344 plies, so 352 = no
+                               limit, as in the reference's recursion; 32 levels live in registers, deeper ones in
+                               the workspace).  A deeper descent sets IFX_F_DEPTH                                   */
+  int32_t num_sims;         /* args.numMCTSSims (MCTS.py:45), < 2^17                              */
   float cpuct;              /* float32(args.cpuct) (MCTS.py:122; NEP-50 weak scalar)              */
   uint64_t seed;            /* Philox key for every random draw on the path    */
   int32_t policy_is_logits; /* 0: nn_pi holds float32 probabilities (NNet.py:94 exp(log_softmax)), nn_v values;
@@ -157,9 +160,11 @@ typedef struct ifx_mcts_layout {
   int64_t hash;       /* uint64 [G][H][2]                                                               */
   int64_t free_stack; /* uint16 [G][C]                                                                  */
   int64_t per_game;   /* struct per game, see csrc/ifx_tree.cuh                                         */
-  int64_t path;       /* uint32x4 [G][32]: {slot<<9|row entry, N word, Q bits, Ns} per path level        */
+  int64_t path;       /* uint32x4 [G][max_depth rounded up to 32]: {slot<<9|row entry, N word, Q bits, Ns}/level */
   int64_t roots;      /* ifx_state [G]                                                                  */
   int64_t leaves;     /* ifx_state [G]                                                                  */
+  int64_t sym;        /* uint8 [G][max(num_sims,128) rounded up to 32][64]: per simulation of the current move, the source
+                         cell of each destination cell under its random_symmetry (byte 63: the symmetry code)  */
   int64_t total;      /* == ifx_mcts_workspace_bytes                                                    */
 } ifx_mcts_layout;
 

@@ -317,3 +317,81 @@ def test_zero_sized_calls_are_noops(backend):
     assert dll.ifx_stub_policy_value(None, 0, None, 0, None, 343, None, None) == 0
     assert dll.ifx_stub_policy_value(None, 1, None, 0, None, 343, None, None) == -1      # IFX_E_ARG
     assert dll.ifx_net_im2col3x3(None, 0, None, None) == 0
+
+
+def sharp_policy_value(planes: torch.Tensor):
+    """A sharply peaked deterministic evaluator: the actions are ranked by a hash of the position and the action ranked
+    r gets the (unnormalised) prior 2^(-4r), value 0 -- the best-ranked VALID move of a node takes >= 15/16 of its prior
+    mass after the masked renormalisation, so the principal variation grows by about one edge per simulation, which is
+    what a confident trained net does to the search.  Powers of two and integer sorting only: the same bits everywhere."""
+    from inflexion_b200.stubnet import _coef, _mix, _MASK31
+    x = planes.reshape(planes.shape[0], 196).to(torch.int64)
+    h = _mix((x * _coef(x.device)).sum(dim=1) & _MASK31)
+    a = torch.arange(343, device=x.device, dtype=torch.int64)
+    z = _mix((h[:, None] + a[None, :] * 0x9E3779B) & _MASK31)
+    rank = torch.argsort(torch.argsort(z * 512 + a[None, :], dim=1), dim=1)         # unique keys: no tie handling involved
+    pi = torch.ldexp(torch.ones_like(rank, dtype=torch.float32), -torch.clamp(4 * rank, max=124).to(torch.int32))
+    return pi, torch.zeros(planes.shape[0], dtype=torch.float32, device=x.device)
+
+
+def test_paths_deeper_than_one_register_chunk_match_oracle(backend):
+    """the reference recurses without limit; with a confident policy the search path passes 32 edges within
+    a few moves at 100 simulations.  Paths beyond the 32 levels a warp holds in registers spill to the workspace; visit
+    counts, sampled actions and the number of live nodes must still equal the oracle's, with the default node pool."""
+    sims, cpuct, seed, moves = 100, 1.0, 11, 4
+
+    def predict(planes):
+        pi, v = sharp_policy_value(torch.from_numpy(np.ascontiguousarray(planes))[None])
+        return pi.numpy()[0], v.numpy()[0]
+    m = BatchedMCTS(2, sims, cpuct, seed=seed, backend=backend)
+    assert m.cfg.max_depth == 352
+    m.reset(start_states(2, 343))
+    deepest = [0]
+    for gi in range(2):
+        it = self_play_moves(predict, sims, cpuct, PhiloxDraws(seed, game=gi), temp_threshold=2, max_moves=moves)
+        if gi == 0:
+            m_search = OracleMCTS.search
+
+            def tracked(self, game, _d=[0]):
+                _d[0] += 1
+                deepest[0] = max(deepest[0], _d[0] - 1)
+                try:
+                    return m_search(self, game)
+                finally:
+                    _d[0] -= 1
+            OracleMCTS.search = tracked
+        try:
+            recs = [next(it) for _ in range(moves)]
+        finally:
+            OracleMCTS.search = m_search
+        if gi == 0:
+            want0 = recs
+        else:
+            want1 = recs
+    assert deepest[0] > 40, deepest                     # well past one register chunk (and past round 1's cap of 32)
+    for mv in range(moves):
+        m.search(sharp_policy_value)
+        m.raise_on_faults()
+        counts = m.root_stats()["counts"].cpu().numpy()
+        acts = m.sample_actions(2)
+        for gi, want in enumerate((want0, want1)):
+            assert np.array_equal(counts[gi], want[mv]["counts"]), (mv, gi)
+            assert int(acts[gi]) == want[mv]["action"], (mv, gi)
+        live = m.status().cpu().numpy()[:, 5]
+        orc, game = want0[mv]["mcts"], want0[mv]["game"]
+        m.advance(acts)
+    # live nodes after the last advance: the oracle's nodes with turn > root turn, or the root itself
+    live = m.status().cpu().numpy()[0, 5]
+    want_live = sum(1 for k in orc.P if np.frombuffer(k, dtype=np.int64)[2 * 49] > game.turn or k == game.key())
+    assert live == want_live
+
+
+def test_max_depth_fault_and_limits(backend):
+    """max_depth below the path the search needs -> IFX_F_DEPTH, loudly; num_sims >= 2^17 is refused."""
+    m = BatchedMCTS(1, 60, 1.0, seed=11, max_depth=8, backend=backend)
+    m.reset(start_states(1, 343))
+    m.search(sharp_policy_value)
+    with pytest.raises(Exception, match="deeper"):
+        m.raise_on_faults()
+    with pytest.raises(Exception):
+        BatchedMCTS(1, 1 << 17, 1.0, backend=backend)
