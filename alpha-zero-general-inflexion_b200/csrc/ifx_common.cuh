@@ -78,6 +78,7 @@ static inline float ifx_fast_exp2f(float x) { return exp2f(x); }
 static inline float ifx_frcp(float x) { return 1.0f / x; }
 static inline float ifx_logf(float x) { return logf(x); }
 static inline float ifx_tanhf(float x) { return tanhf(x); }
+static inline float ifx_tanh_fast(float x) { return tanhf(x); }
 static inline float ifx_cosf(float x) { return cosf(x); }
 static inline float ifx_powf(float x, float y) { return powf(x, y); }
 static inline float ifx_noise_logf(float x) { return logf(x); }
@@ -91,6 +92,14 @@ IFX_D float ifx_fast_exp2f(float x) {                           // one MUFU.EX2 
 IFX_D float ifx_frcp(float x) { return __frcp_rn(x); }
 IFX_D float ifx_logf(float x) { return logf(x); }
 IFX_D float ifx_tanhf(float x) { return tanhf(x); }
+// tanh(x) = 1 - 2 / (2^(2x log2 e) + 1) with MUFU.EX2 / MUFU.RCP: absolute error ~2e-7 (fused-head path only, whose
+// agreement with the fp32 module is a 1e-3 tolerance); saturates correctly at +-1
+IFX_D float ifx_tanh_fast(float x) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
 // noise-only helpers: the fast intrinsics (no slow paths, no local memory); their accuracy is ample for a random draw
 IFX_D float ifx_cosf(float x) { return __cosf(x); }
 IFX_D float ifx_powf(float x, float y) { return __powf(x, y); }
@@ -167,11 +176,11 @@ IFX_D void lanes_bfly_fadd(LaneVar<float>& x, int mask) {
   x.v = __fadd_rn(x.v, __shfl_xor_sync(0xffffffffu, x.v, mask));
 }
 template <class T> IFX_D T lanes_bcast(const LaneVar<T>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
-IFX_D float lanes_max_f32(const LaneVar<float>& x) {
-  float m = x.v;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  return m;
+IFX_D float lanes_max_f32(const LaneVar<float>& x) {          // one REDUX on keys that sort like the floats (NaN-free input)
+  uint32_t k = __float_as_uint(x.v);
+  k = (k & 0x80000000u) ? ~k : (k | 0x80000000u);
+  const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);
+  return __uint_as_float((kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax);
 }
 IFX_D float lanes_sum_f32(const LaneVar<float>& x) {
   float t = x.v;

@@ -505,8 +505,12 @@ IFX_D float tree_pairwise_sum343(const float* buf) {
 // order, from which the action of any compact row entry follows in a few instructions.
 struct alignas(16) ExpandScratch { float buf[IFX_ROW]; uint8_t own_cell[64]; uint8_t spawn_cell[64]; };
 
-// exact mode: pi row (float32, >= 343 entries) -> buf.  Issued with the first round trip.
-IFX_D void tree_stage_policy(const float* pi, bool aligned, float* buf) {
+// The row travels in two steps so that its loads can be ISSUED with the first round trip of the wave (before anything
+// waits on the game record) and STORED to shared memory once they have landed: a warp issues in order, so a store
+// placed right behind its load would hold back every later load by a full round trip.
+struct StagedRow { LaneVar<IfxF4> f[3]; };                   // exact mode: 12 floats per lane; fused mode: f[0..1] hold 12 halfs
+// exact mode: pi row (float32, >= 343 entries)
+IFX_D void tree_stage_policy_load(const float* pi, bool aligned, StagedRow& R) {
   IFX_FOR_LANES(l) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -520,18 +524,46 @@ IFX_D void tree_stage_policy(const float* pi, bool aligned, float* buf) {
         if (i + 2 < IFX_ACTIONS) v.z = pi[i + 2];
         if (i + 3 < IFX_ACTIONS) v.w = pi[i + 3];
       }
-      if (i < IFX_ROW) *reinterpret_cast<IfxF4*>(buf + i) = v;
+      R.f[j][l] = v;
     }
   }
 }
-// fused mode: binary16 head row (343 logits + the value pre-activation, 8-byte aligned) -> lower half of buf
-IFX_D void tree_stage_head(const uint16_t* head, float* buf) {
-  uint16_t* sh = reinterpret_cast<uint16_t*>(buf);
+IFX_D void tree_stage_policy_store(const StagedRow& R, float* buf) {
   IFX_FOR_LANES(l) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int i = 4 * l + 128 * j;
-      if (i < 344) *reinterpret_cast<uint2*>(sh + i) = *reinterpret_cast<const uint2*>(head + i);
+      if (i < IFX_ROW) *reinterpret_cast<IfxF4*>(buf + i) = R.f[j][l];
+    }
+  }
+}
+// fused mode: binary16 head row (343 logits + the value pre-activation, 8-byte aligned) -> lower half of buf
+IFX_D void tree_stage_head_load(const uint16_t* head, StagedRow& R) {
+  IFX_FOR_LANES(l) {
+    uint2 h[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      h[j].x = 0u; h[j].y = 0u;
+      if (i < 344) h[j] = *reinterpret_cast<const uint2*>(head + i);
+    }
+    IfxF4 a, b;
+    a.x = ifx_u2f(h[0].x); a.y = ifx_u2f(h[0].y); a.z = ifx_u2f(h[1].x); a.w = ifx_u2f(h[1].y);
+    b.x = ifx_u2f(h[2].x); b.y = ifx_u2f(h[2].y); b.z = 0.0f; b.w = 0.0f;
+    R.f[0][l] = a; R.f[1][l] = b;
+  }
+}
+IFX_D void tree_stage_head_store(const StagedRow& R, float* buf) {
+  uint16_t* sh = reinterpret_cast<uint16_t*>(buf);
+  IFX_FOR_LANES(l) {
+    const IfxF4 a = R.f[0][l], b = R.f[1][l];
+    uint2 h[3];
+    h[0].x = ifx_f2u(a.x); h[0].y = ifx_f2u(a.y); h[1].x = ifx_f2u(a.z); h[1].y = ifx_f2u(a.w);
+    h[2].x = ifx_f2u(b.x); h[2].y = ifx_f2u(b.y);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = 4 * l + 128 * j;
+      if (i < 344) *reinterpret_cast<uint2*>(sh + i) = h[j];
     }
   }
 }
@@ -596,25 +628,39 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
   float total, scale = 0.0f, mb = 0.0f;
   const float L2E = 1.4426950408889634f;
   uint16_t* sh = reinterpret_cast<uint16_t*>(buf);          // fused: staged halfs [0,344), compact valid logits [352, 352+nv)
+  // A lane's first four entries (all it has when nv <= 128, i.e. nearly always) stay in registers through the three
+  // steps -- gather, exp / sum, scale / store -- as four independent chains; entries beyond 128 take a plain loop over
+  // the compact copy in shared memory.
+  LaneVar<IfxF4> xs;
   if (fused) {
-    *leaf_v = ifx_tanhf(ifx_h2f(sh[IFX_ACTIONS]));
+    *leaf_v = ifx_tanh_fast(ifx_h2f(sh[IFX_ACTIONS]));
     LaneVar<float> lmax;
     IFX_FOR_LANES(l) {
-      float mx = -INFINITY;
-      for (int ci = l; ci < V.nv; ci += 32) {
+      float x[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ci = l + 32 * t;
+        x[t] = ci < V.nv ? ifx_h2f(sh[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)]) : -INFINITY;
+      }
+      float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+      for (int ci = l + 128; ci < V.nv; ci += 32) {
         const uint16_t hx = sh[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)];
         sh[IFX_ROW + ci] = hx;
         mx = fmaxf(mx, ifx_h2f(hx));
       }
-      lmax[l] = mx;
+      IfxF4 xv; xv.x = x[0]; xv.y = x[1]; xv.z = x[2]; xv.w = x[3];
+      xs[l] = xv; lmax[l] = mx;
     }
     const float m = lanes_max_f32(lmax);
     mb = -m * L2E;
     LaneVar<float> part;
-    IFX_FOR_LANES(l) {
-      float acc = 0.0f;                                     // exp(x - m) = 2^((x - m) * log2(e)): one multiply-add and one MUFU.EX2
-      for (int ci = l; ci < V.nv; ci += 32) acc += ifx_fast_exp2f(fmaf(ifx_h2f(sh[IFX_ROW + ci]), L2E, mb));
-      part[l] = acc;
+    IFX_FOR_LANES(l) {                                      // exp(x - m) = 2^((x - m) * log2(e)): one multiply-add and one MUFU.EX2
+      IfxF4 e = xs[l];                                      // (entries beyond nv hold -inf: 2^-inf = 0)
+      e.x = ifx_fast_exp2f(fmaf(e.x, L2E, mb)); e.y = ifx_fast_exp2f(fmaf(e.y, L2E, mb));
+      e.z = ifx_fast_exp2f(fmaf(e.z, L2E, mb)); e.w = ifx_fast_exp2f(fmaf(e.w, L2E, mb));
+      float acc = (e.x + e.y) + (e.z + e.w);
+      for (int ci = l + 128; ci < V.nv; ci += 32) acc += ifx_fast_exp2f(fmaf(ifx_h2f(sh[IFX_ROW + ci]), L2E, mb));
+      xs[l] = e; part[l] = acc;
     }
     total = lanes_sum_f32(part);                            // float32 net output: any summation order is within tolerance
   } else {
@@ -628,15 +674,29 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
   if (G.leaf_hpos < 0) { G.faults |= IFX_F_HASH; return -1; }
   float* prow = tree_row(P, g, slot, 0);
   float* nrow = tree_row(P, g, slot, 1);
-  IFX_FOR_LANES(l) {
-    for (int ci = l; ci < V.nv; ci += 32) {                 // coalesced: consecutive lanes, consecutive row entries
-      float p;
-      if (fused) {
-        p = uniform ? scale : ifx_fast_exp2f(fmaf(ifx_h2f(sh[IFX_ROW + ci]), L2E, mb)) * scale;
-      } else {                                              // policies /= sum (policies = valids in the fallback, MCTS.py:105)
-        p = ifx_fdiv(uniform ? 1.0f : buf[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)], total);
+  IFX_FOR_LANES(l) {                                        // stores are coalesced: consecutive lanes, consecutive row entries
+    if (fused) {
+      const IfxF4 e = xs[l];
+      if (l < V.nv) prow[l] = uniform ? scale : e.x * scale;
+      if (l + 32 < V.nv) prow[l + 32] = uniform ? scale : e.y * scale;
+      if (l + 64 < V.nv) prow[l + 64] = uniform ? scale : e.z * scale;
+      if (l + 96 < V.nv) prow[l + 96] = uniform ? scale : e.w * scale;
+      for (int ci = l + 128; ci < V.nv; ci += 32)
+        prow[ci] = uniform ? scale : ifx_fast_exp2f(fmaf(ifx_h2f(sh[IFX_ROW + ci]), L2E, mb)) * scale;
+    } else {                                                // policies /= sum (policies = valids in the fallback, MCTS.py:105)
+      float v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ci = l + 32 * t;
+        v[t] = (ci < V.nv && !uniform) ? buf[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)] : 1.0f;
       }
-      prow[ci] = p;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {                         // (a dummy 1.0 keeps idle lanes out of the division's slow path)
+        const float q = ifx_fdiv(v[t], total);
+        if (l + 32 * t < V.nv) prow[l + 32 * t] = q;
+      }
+      for (int ci = l + 128; ci < V.nv; ci += 32)
+        prow[ci] = ifx_fdiv(uniform ? 1.0f : buf[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)], total);
     }
     const IfxU4 z = {IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH, IFX_N_FRESH};   // Nsa = 0 for every valid action
     for (int c4 = 4 * l; c4 < V.nv; c4 += 128) *reinterpret_cast<IfxU4*>(nrow + c4) = z;
@@ -775,18 +835,15 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
   // round trip 1: everything whose address is known up front, issued together (leaf / policy / value are
   // speculative: they are only used when a leaf is pending, which is the common case)
   IfxGame G = P.games[g];
-  // the root's rows start moving into shared memory the moment the record is here; they land while the pending
-  // leaf is expanded and backed up
-  int mirror_slot = G.root_slot;
-  if (mirror_slot >= 0) tree_mirror_fetch(P, g, mirror_slot, G.root_nv, mirror);
   const ifx_state leaf = P.leaves[g];
   float leaf_v = 0.0f;
+  StagedRow staged;
   if (P.logits == 2) {                                      // binary16 head output: exp + tanh are fused into the expansion
-    tree_stage_head(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g0 * pi_stride, scratch->buf);
+    tree_stage_head_load(reinterpret_cast<const uint16_t*>(nn_pi) + (int64_t)g0 * pi_stride, staged);
   } else {
     leaf_v = nn_v[g0];
     const float* pi_row = nn_pi + (int64_t)g0 * pi_stride;
-    tree_stage_policy(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, scratch->buf);
+    tree_stage_policy_load(pi_row, (pi_stride & 3) == 0 && pi_stride >= IFX_ROW && ((uintptr_t)nn_pi & 15) == 0, staged);
   }
   LaneVar<IfxU4> path;
   // the first 8 levels of the pending leaf's path travel with the first round trip (one 128-byte line); deeper
@@ -796,6 +853,12 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
     if (l < 8) e = P.path[(int64_t)g * P.path_stride + l];
     path[l] = e;
   }
+  // -- everything above is in flight; the first USE of the record comes only now (a warp issues in order) --
+  // the root's rows (and the root position) start moving into shared memory the moment the record is here; they land
+  // while the pending leaf is expanded and backed up
+  int mirror_slot = G.root_slot;
+  if (mirror_slot >= 0) tree_mirror_fetch(P, g, mirror_slot, G.root_nv, mirror);
+  if (P.logits == 2) tree_stage_head_store(staged, scratch->buf); else tree_stage_policy_store(staged, scratch->buf);
   if (G.pending && G.path_len > 8) {
     IFX_FOR_LANES(l) { if (l >= 8) path[l] = P.path[(int64_t)g * P.path_stride + l]; }
   }
