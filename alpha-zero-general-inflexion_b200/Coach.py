@@ -106,11 +106,9 @@ class Coach:
                              temp_threshold=int(self.args.tempThreshold), seed=seed, max_turns=self.game._max_turns,
                              game_id_base=game_id_base + rank * per, fused_head=fused,
                              nodes_per_game=dict(self.args).get("nodesPerGame", "auto"))
-        if world > 1:                                   # every rank plays the full episode length (all-gather shapes agree)
-            while eng.move < eng.max_moves:
-                eng.play_move()
-        else:
-            eng.play_episode()
+        # the ranks stop together, as soon as every game everywhere is over (all-gather shapes agree; no rank keeps
+        # searching finished games)
+        eng.play_episode(collective=world > 1)
         eng.mcts.raise_on_faults()
         rec = eng.gather_records() if gather else eng.records()
         if compact:

@@ -29,13 +29,19 @@ log = logging.getLogger(__name__)
 
 
 class MCTS:
-    def __init__(self, nnet, args, seed: int | None = None, backend=None):
+    def __init__(self, nnet, args, seed: int | None = None, backend=None, game_id: int = 0):
         if not hasattr(nnet, "predict"):
             raise TypeError("nnet must provide predict(planes) (NeuralNet.py:27-38)")
         self.nnet = nnet
         self.args = args
         self._backend = backend
+        # Random draws (leaf symmetries, arg-max tie-break) are Philox values keyed by (seed; game_id, move, simulation).
+        # Without a seed every object draws its own from numpy's global stream, like the reference's use of np.random;
+        # with one, the searches are reproducible and ``reset()`` hands out consecutive game ids (Arena resets the
+        # player once per game: game i is searched on stream i, as BatchedArena does).
+        self._seeded = seed is not None
         self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._game_id, self._resets = int(game_id), 0
         self._tree: BatchedMCTS | None = None
         self._last_turn = -1
 
@@ -52,7 +58,7 @@ class MCTS:
     def _install_root(self, game) -> None:
         sims, cpuct = int(self.args.numMCTSSims), self.args.cpuct
         state = game._state.copy()
-        state["tag"] = 0
+        state["tag"] = self._game_id
         if self._tree is None:
             self._tree = BatchedMCTS(1, sims, cpuct, seed=self._seed, backend=self._backend,
                                      nodes_per_game=min(16383, max(4096, 16 * sims)),
@@ -98,7 +104,10 @@ class MCTS:
             self.args["numMCTSSims"] = saved
 
     def reset(self):
-        return MCTS(self.nnet, self.args, backend=self._backend)          # MCTS.py:147-148
+        if not self._seeded:
+            return MCTS(self.nnet, self.args, backend=self._backend)      # MCTS.py:147-148
+        self._resets += 1
+        return MCTS(self.nnet, self.args, seed=self._seed, backend=self._backend, game_id=self._game_id + self._resets - 1)
 
     def dump(self) -> dict:
         """Root tables of the last search (the reference's Qsa/Nsa/Ns for the root state)."""

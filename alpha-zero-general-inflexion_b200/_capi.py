@@ -64,6 +64,9 @@ PROTOTYPES = {
     "ifx_mcts_status": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_get_roots": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_counters": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ifx_mcts_live_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ifx_gather_pack_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "ifx_gather_scatter_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "ifx_net_im2col3x3": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ifx_stub_policy_value": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
 }

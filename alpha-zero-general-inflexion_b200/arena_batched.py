@@ -20,12 +20,15 @@ from .state import STATE_DTYPE, pack_states
 
 class BatchedArena:
     def __init__(self, evaluate, num_sims: int, cpuct=1.0, opponent: str = "random", seed: int = 0,
-                 max_turns: int = 343, backend: Backend | None = None, fused_head: bool = False):
+                 max_turns: int = 343, backend: Backend | None = None, fused_head: bool = False, record: bool = False):
         if opponent not in ("random", "greedy"):
             raise ValueError("opponent must be 'random' or 'greedy'")
         self.be = backend or default_backend()
         self.evaluate, self.num_sims, self.cpuct = evaluate, int(num_sims), cpuct
         self.opponent, self.seed, self.max_turns, self.fused_head = opponent, int(seed), int(max_turns), fused_head
+        # record: keep every game's move sequence and result of the last playGames call (this rank's games):
+        # ``last_actions`` int32 [plies, games] (-1 once a game is over), ``last_results`` (+1 RED won, -1 BLUE, 0 draw)
+        self.record, self.last_actions, self.last_results = bool(record), None, None
 
     def _opponent_actions(self, states, ply):
         if self.opponent == "random":
@@ -61,8 +64,8 @@ class BatchedArena:
                              tags=np.arange(lo, hi))
         states = self.be.states_tensor(starts)
         mcts = BatchedMCTS(num, self.num_sims, self.cpuct, seed=self.seed, backend=self.be, fused_head=self.fused_head)
-        red_first_t = torch.from_numpy(red_first).to(self.be.device)
         started = False
+        played = []
         for ply in range(self.max_turns + 2):
             outcome = states[:, 45]
             if bool((outcome != 0).all()):
@@ -78,7 +81,7 @@ class BatchedArena:
                     started = True
                 else:
                     mcts.set_roots(roots)
-                mcts.search(self.evaluate)
+                mcts.search(self.evaluate, pack=True)                            # the net sees only the games RED moves in
                 acts_red = mcts.sample_actions(0)                                # temp = 0: arg-max, ties uniformly
             else:
                 acts_red = torch.full((num,), -1, dtype=torch.int32, device=self.be.device)
@@ -86,6 +89,8 @@ class BatchedArena:
             acts = torch.where(red_to_move, acts_red, acts_blue).to(torch.int32).contiguous()
             _, nxt, status = rules.mask_step(states, acts, want_masks=False, backend=self.be)
             live = (outcome == 0)
+            if self.record:
+                played.append(torch.where(live, acts, torch.full_like(acts, -1)))
             if bool((status[live] != 0).any()):
                 raise RuntimeError("a player produced an invalid action")       # Arena.py:65-68
             states = nxt
@@ -97,4 +102,7 @@ class BatchedArena:
         mover_red = final["player"] == 0
         red_won = ((final["outcome"] == 2) & mover_red) | ((final["outcome"] == 3) & ~mover_red)
         blue_won = ((final["outcome"] == 2) & ~mover_red) | ((final["outcome"] == 3) & mover_red)
+        if self.record:
+            self.last_actions = torch.stack(played).cpu().numpy() if played else np.zeros((0, num), np.int32)
+            self.last_results = red_won.astype(np.int64) - blue_won.astype(np.int64)
         return int(red_won.sum()), int(blue_won.sum()), int((final["outcome"] == 1).sum())

@@ -209,6 +209,8 @@ IFX_D void lanes_argmax(const LaneVar<float>& u, const LaneVar<int>& a, float* b
 // ---------------------------------------------------------------------------------------------
 // constants of the game (inflexion/InflexionGame.py:14-21, 47-50, 68; main.py:34)
 // ---------------------------------------------------------------------------------------------
+struct alignas(16) IfxVec16 { uint32_t x, y, z, w; };
+
 #define IFX_N 7
 #define IFX_CELLS 49
 #define IFX_MOVES 7

@@ -1012,15 +1012,18 @@ IFX_D uint64_t ifx_cas64(uint64_t* p, uint64_t expect, uint64_t desired) {
 // ---- start of a move: reclaim nodes the new root can no longer reach, rebuild hash + free stack ----
 // A node is reachable only if its turn plane exceeds the root's (the key contains the turn), or it is the
 // root itself.  Survivors are re-inserted 32 at a time (one per lane, claimed by CAS).
-IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all) {
+IFX_D void tree_begin_move(const TreeParams& P, int g, bool clear_all, bool prev_searched = true) {
   IfxGame G = P.games[g];
   const ifx_state root = P.roots[g];
   if (clear_all) {                                          // MCTS.__init__ / reset (MCTS.py:21-31,147-148)
     IfxGame Z; memset(&Z, 0, sizeof(Z));
     Z.game_id = root.tag;
     G = Z;
-  } else {
-    G.move_idx += 1;                                        // next getActionProb on the same tables
+  } else if (prev_searched) {
+    // next getActionProb on the same tables.  The move coordinate of the random draws counts the moves this tree has
+    // SEARCHED (the k-th getActionProb call of a reference MCTS object): a root handed over as finished -- Arena gives
+    // the search only the games in which its player is to move -- does not advance it.
+    G.move_idx += 1;
   }
   IfxKey* tab = P.hash + (int64_t)g * P.H;
   IfxKey* keys = P.node_key + (int64_t)g * P.C;

@@ -46,9 +46,11 @@ IFX_D void body_reset(const TreeParams& P, int g, const ifx_state* roots, const 
 }
 
 IFX_D void body_set_roots(const TreeParams& P, int g, const ifx_state* roots) {
+  const bool searched = P.roots[g].outcome == IFX_ONGOING;   // was the previous root one the search worked on?
+  IFX_SYNCWARP();
   if (IFX_LANE0) P.roots[g] = roots[g];
   IFX_SYNCWARP();
-  tree_begin_move(P, g, false);
+  tree_begin_move(P, g, false, searched);
 }
 
 IFX_D void body_advance(const TreeParams& P, int g, const int32_t* actions) {
@@ -218,6 +220,30 @@ __global__ void tree_counters_kernel(TreeParams P, unsigned long long* __restric
   atomicAdd(&acc[0], v); atomicAdd(&acc[1], e); atomicAdd(&acc[2], t); atomicAdd(&acc[3], s);
   __syncthreads();
   if (threadIdx.x < 4) out[threadIdx.x] = acc[threadIdx.x];
+}
+// games that will search in the coming move (root ongoing, simulations left, no fault), ascending; one block, two passes
+__global__ void __launch_bounds__(1024) tree_live_rows_kernel(TreeParams P, int32_t* __restrict__ live_idx, int32_t* __restrict__ count) {
+  __shared__ int32_t part[1024];
+  const int t = threadIdx.x, per = (P.G + 1023) / 1024, lo = t * per, hi = min(P.G, lo + per);
+  int n = 0;
+  for (int g = lo; g < hi; ++g) {
+    const IfxGame G = P.games[g];
+    n += (P.roots[g].outcome == IFX_ONGOING && G.sims_done < P.num_sims && !G.faults) ? 1 : 0;
+  }
+  part[t] = n;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {                 // inclusive scan (Hillis-Steele)
+    const int v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int pos = part[t] - n;
+  for (int g = lo; g < hi; ++g) {
+    const IfxGame G = P.games[g];
+    if (P.roots[g].outcome == IFX_ONGOING && G.sims_done < P.num_sims && !G.faults) live_idx[pos++] = g;
+  }
+  if (t == 1023) *count = part[1023];
 }
 #define TREE_GRID(P) ((unsigned)(((P).G + TREE_WARPS - 1) / TREE_WARPS))
 #endif
@@ -447,6 +473,22 @@ int ifx_mcts_get_roots(ifx_mcts* m, ifx_state* roots, void* stream) {
 #else
   const int64_t n = (int64_t)m->P.G * 4;
   tree_get_roots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m->P, reinterpret_cast<uint4*>(roots));
+  return ifx_after_launch();
+#endif
+}
+
+int ifx_mcts_live_rows(ifx_mcts* m, int32_t* live_idx, int32_t* count, void* stream) {
+  if (!m || !live_idx || !count) return IFX_E_ARG;
+#ifdef IFX_HOSTSIM
+  int32_t n = 0;
+  for (int g = 0; g < m->P.G; ++g) {
+    const IfxGame& G = m->P.games[g];
+    if (m->P.roots[g].outcome == IFX_ONGOING && G.sims_done < m->P.num_sims && !G.faults) live_idx[n++] = g;
+  }
+  *count = n;
+  return ifx_after_launch();
+#else
+  tree_live_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(m->P, live_idx, count);
   return ifx_after_launch();
 #endif
 }

@@ -51,11 +51,13 @@ class BatchedMCTS:
     def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | str | None = None,
                  max_depth: int = 352, backend: Backend | None = None, fused_head: bool = False,
                  pad_policy_rows: bool = True, terminal_sims_per_wave: int = 1, dirichlet_alpha: float = 0.0,
-                 dirichlet_eps: float = 0.0):
+                 dirichlet_eps: float = 0.0, pack_quantum: int | None = None):
         """fused_head: the net hands over its last GEMM output (float16 [G,344]: 343 policy logits + the value
         pre-activation, buffer ``nn_head``) and the tree kernel applies softmax / tanh itself.
         terminal_sims_per_wave: how many simulations that end in a terminal state (no net needed) a game may run in
         one wave before it yields (0 = no limit); results do not depend on it, the length of a wave's tail does.
+        pack_quantum: granularity of the packed net batch (see ``plan_rows``); None = 256 rows from 2048 games on, 32 rows
+        from 64 games on, otherwise no packing; 0 = never pack.
         dirichlet_alpha / dirichlet_eps: optional root noise P <- (1-eps) P + eps Dir(alpha), drawn on the device once
         per move.  The reference's MCTS has none, so the default (eps = 0) is off and the bit-exact parity holds."""
         self.be = backend or default_backend()
@@ -97,6 +99,16 @@ class BatchedMCTS:
         self.nn_head = self.be.zeros((g, 344), torch.float16) if fused_head else None
         self.waves_run = 0
         self.evals_run = 0
+        self.rows_evaluated = 0                                 # net rows evaluated so far (evals x active rows)
+        # leaf gather: the games that search in the current move, and the packed net buffers per batch size
+        if pack_quantum is None:
+            pack_quantum = 256 if g >= 2048 else (32 if g >= 64 else 0)
+        self.pack_quantum = int(pack_quantum)
+        self._live_idx = self.be.zeros((g,), torch.int32)
+        self._live_n = self.be.zeros((1,), torch.int32)
+        self.live_count = g
+        self.rows_active = g                                    # rows the net runs on in the current move (g = dense)
+        self._packed = {}
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -142,8 +154,61 @@ class BatchedMCTS:
                                                     self.nn_v.data_ptr(), self.nn_in.data_ptr(), self.be.stream()))
         self.waves_run += 1
 
+    # ---- leaf gather (north_star kernel 3) -----------------------------------------------------------
+    def plan_rows(self) -> int:
+        """Decide the net batch of the coming move.  Lists the games that will search (root not over, simulations left:
+        ``ifx_mcts_live_rows``), reads their number (ONE host sync per move) and rounds it up to ``pack_quantum``.  When
+        that is below the game count, every ``feed`` of the move packs the live games' planes into the first rows of a
+        batch of that size, runs the net on it and scatters the answers back -- the reference evaluates one leaf per
+        real simulation only (MCTS.py:89-93).  Returns the batch size (``n_games`` = dense, no packing).
+        Call after reset / set_roots / advance; without a call the batch stays dense."""
+        self.be.check(self.be.dll.ifx_mcts_live_rows(self._h, self._live_idx.data_ptr(), self._live_n.data_ptr(), self.be.stream()))
+        self.live_count = int(self._live_n.item())
+        q, g = self.pack_quantum, self.n_games
+        rows = g if q <= 0 else min(g, max(q, -(-self.live_count // q) * q))
+        self.rows_active = rows
+        return rows
+
+    def dense_rows(self) -> None:
+        self.rows_active, self.live_count = self.n_games, self.n_games
+
+    def _packed_buffers(self, rows: int):
+        if rows not in self._packed:
+            b = {"in": self.be.zeros((rows, 4, 7, 7), torch.float32)}
+            if self.fused_head:
+                b["head"] = self.be.zeros((rows, 344), torch.float16)
+            else:
+                b["pi"] = self.be.zeros((rows, 352), torch.float32)
+                b["v"] = self.be.zeros((rows,), torch.float32)
+            self._packed[rows] = b
+        return self._packed[rows]
+
+    def _move_rows(self, fn, src, dst, rows: int, row_bytes: int) -> None:
+        self.be.check(fn(src.data_ptr(), src.stride(0) * src.element_size(), self._live_idx.data_ptr(), self._live_n.data_ptr(),
+                         rows, row_bytes, dst.data_ptr(), dst.stride(0) * dst.element_size(), self.be.stream()))
+
+    def _feed_packed(self, evaluate, rows: int) -> None:
+        dll, b = self.be.dll, self._packed_buffers(rows)
+        self._move_rows(dll.ifx_gather_pack_rows, self.nn_in, b["in"], rows, 196 * 4)
+        if self.fused_head:
+            evaluate(b["in"], b["head"])
+            self._move_rows(dll.ifx_gather_scatter_rows, b["head"], self.nn_head, rows, 344 * 2)
+        else:
+            pi, v = evaluate(b["in"])
+            b["pi"][:, :343].copy_(pi)
+            b["v"].copy_(v.reshape(-1))
+            padded = hasattr(self, "_nn_pi_rows")
+            self._move_rows(dll.ifx_gather_scatter_rows, b["pi"], self._nn_pi_rows if padded else self.nn_pi, rows,
+                            (344 if padded else 343) * 4)
+            self._move_rows(dll.ifx_gather_scatter_rows, b["v"], self.nn_v, rows, 4)
+
     def feed(self, evaluate) -> None:
         """One net evaluation of the pending leaves into the buffers the next wave reads."""
+        self.rows_evaluated += self.rows_active
+        if self.rows_active < self.n_games:
+            self._feed_packed(evaluate, self.rows_active)
+            self.evals_run += 1
+            return
         if self.fused_head:
             evaluate(self.nn_in, self.nn_head)              # writes float16 [G,344] in place
         else:
@@ -154,8 +219,11 @@ class BatchedMCTS:
                 self.nn_v.copy_(v.reshape(-1))
         self.evals_run += 1
 
-    def search(self, evaluate) -> None:
-        """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync."""
+    def search(self, evaluate, pack: bool = False) -> None:
+        """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync, unless
+        ``pack``: then ``plan_rows`` first (one sync) so the net only sees the games that search in this move."""
+        if pack:
+            self.plan_rows()
         for _ in range(self.waves_per_search - 1):
             self.wave()
             self.feed(evaluate)

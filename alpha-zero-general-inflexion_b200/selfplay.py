@@ -51,7 +51,10 @@ class SelfPlayEngine:
             self.ex_counts = self.be.empty((self.max_moves, self.G, 343), torch.int32)
             self.ex_actions = self.be.empty((self.max_moves, self.G), torch.int32)
         self.use_graph = self.be.is_cuda if use_graph is None else bool(use_graph)
-        self._graph = None
+        self._graphs = {}                                         # net batch size -> captured search of one move
+        # fixed sets of episodes (no auto_restart) thin out as games end: the net then runs on the live games only
+        # (BatchedMCTS.plan_rows: one host read per move, a captured graph per batch size)
+        self.pack = not self.auto_restart
         self.move = 0
         self.my_launches = 0                                      # kernels of libifx_b200 launched (bench evidence)
         self.extra_launches_per_search = 0                        # library kernels inside `evaluate` (the stub evaluator)
@@ -76,18 +79,20 @@ class SelfPlayEngine:
         s = torch.cuda.Stream(device=self.be.device)
         s.wait_stream(torch.cuda.current_stream(self.be.device))
         with torch.cuda.stream(s):
+            rows = self.mcts.rows_active
             for _ in range(2):                                   # warm the allocator / cuDNN heuristics (results unused)
                 if self.mcts.fused_head:
-                    self.evaluate(self.mcts.nn_in, torch.empty_like(self.mcts.nn_head))
+                    self.evaluate(self.mcts.nn_in[:rows], torch.empty_like(self.mcts.nn_head[:rows]))
                 else:
-                    self.evaluate(self.mcts.nn_in)
+                    self.evaluate(self.mcts.nn_in[:rows])
         torch.cuda.current_stream(self.be.device).wait_stream(s)
         torch.cuda.synchronize(self.be.device)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
             for _ in range(self.mcts.waves_per_search - 1):
                 self._wave_and_net()
             self.mcts.wave()
+        self._graphs[self.mcts.rows_active] = graph
 
     def search(self, wave_timer=None) -> None:
         """The numMCTSSims loop for all games.  ``wave_timer`` (optional): True launches every tree wave outside the
@@ -95,10 +100,12 @@ class SelfPlayEngine:
         launch instead."""
         if wave_timer is True:
             wave_timer = lambda fn: fn()  # noqa: E731
+        if self.pack and self.mcts.plan_rows() and self.mcts.live_count == 0:
+            return                                               # every game is over: nothing to search
         if self.use_graph and wave_timer is None:
-            if self._graph is None:
+            if self.mcts.rows_active not in self._graphs:
                 self._capture()
-            self._graph.replay()
+            self._graphs[self.mcts.rows_active].replay()
         elif wave_timer is None:
             for _ in range(self.mcts.waves_per_search - 1):
                 self._wave_and_net()
@@ -143,16 +150,30 @@ class SelfPlayEngine:
         self.search(wave_timer)
         return self.finish_move()
 
-    def play_episode(self, max_moves: int | None = None) -> int:
-        """Play until every game is over (or ``max_moves``); returns the number of moves played."""
+    def play_episode(self, max_moves: int | None = None, collective: bool = False) -> int:
+        """Play until every game is over (or ``max_moves``); returns the number of moves played.
+
+        ``collective`` (under torch.distributed): the ranks decide TOGETHER when to stop -- an all-reduce of two flags
+        every 16 moves -- so every rank plays the same number of moves (``gather_records`` needs equal shapes) and none
+        plays on after all games everywhere have ended; a fault on any rank raises on every rank."""
         limit = self.max_moves if max_moves is None else min(max_moves, self.max_moves)
+        dist = None
+        if collective:
+            import torch.distributed as dist_mod
+            if dist_mod.is_available() and dist_mod.is_initialized() and dist_mod.get_world_size() > 1:
+                dist = dist_mod
         while self.move < limit:
             self.play_move()
             if self.move % 16 == 0 or self.move == limit:
                 st = self.mcts.status()
-                if bool((st[:, 2] != 0).any()):
+                flags = torch.stack([(st[:, 2] != 0).any(), (st[:, 4] == 0).any()]).to(torch.int32)   # [fault, someone plays]
+                if dist is not None:
+                    dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+                fault, playing = (bool(x) for x in flags.tolist())
+                if fault:
                     self.mcts.raise_on_faults()
-                if bool((st[:, 4] != 0).all()):
+                    raise RuntimeError("MCTS fault on another rank")
+                if not playing:
                     break
         return self.move
 

@@ -57,7 +57,8 @@ def stub_kernel_evaluator(mcts, mode: str = "float"):
         be.check(be.dll.ifx_stub_policy_value(nn_in.data_ptr(), nn_in.shape[0], coef.data_ptr(), int(mode == "dyadic"),
                                               mcts.nn_pi.data_ptr(), mcts.nn_pi.stride(0), mcts.nn_v.data_ptr(),
                                               be.stream()))
-        return mcts.nn_pi, mcts.nn_v
+        n = nn_in.shape[0]                                    # (a packed batch is smaller than the game count: views of its rows)
+        return (mcts.nn_pi, mcts.nn_v) if n == mcts.n_games else (mcts.nn_pi[:n], mcts.nn_v[:n])
     return evaluate
 
 

@@ -234,6 +234,25 @@ IFX_API int ifx_mcts_get_roots(ifx_mcts* m, ifx_state* roots, void* stream);
 /* counters uint64 [4]: node visits V (expanded nodes traversed), expansions E, terminal leaves, simulations. */
 IFX_API int ifx_mcts_counters(ifx_mcts* m, uint64_t* counters, void* stream);
 
+/* ---- leaf gather: one contiguous batch for the policy/value net ------------------------------- */
+
+/* The games that will search in the coming move -- root not terminal, simulations left, no fault -- in ascending
+ * order: live_idx int32 [G] (first *count entries valid), count int32 [1] (device).  The reference calls the net once
+ * per real leaf only (MCTS.py:89-93); with this list and the two row movers below the batched net forward runs on the
+ * live games' rows instead of on all G (episode tails, Arena).  Call after reset / set_roots / advance. */
+IFX_API int ifx_mcts_live_rows(ifx_mcts* m, int32_t* live_idx, int32_t* count, void* stream);
+
+/* dst[k] = src[idx[k]] for k < *n_ptr; rows *n_ptr <= k < rows_cap of dst are zeroed.  Rows are row_bytes long
+ * (a multiple of 4; the copy runs 16 bytes at a time when rows, strides and bases are multiples of 16), strides in
+ * bytes, all pointers device pointers; n_ptr is read
+ * on the DEVICE so a captured CUDA graph serves any live count up to rows_cap.
+ * Use: nn_in rows [G][4][7][7] float32 of the live games -> packed [rows_cap][4][7][7]. */
+IFX_API int ifx_gather_pack_rows(const void* src, int64_t src_stride, const int32_t* idx, const int32_t* n_ptr,
+                                 int64_t rows_cap, int64_t row_bytes, void* dst, int64_t dst_stride, void* stream);
+/* dst[idx[k]] = src[k] for k < *n_ptr (the inverse: the net's packed output rows back to the games' rows). */
+IFX_API int ifx_gather_scatter_rows(const void* src, int64_t src_stride, const int32_t* idx, const int32_t* n_ptr,
+                                    int64_t rows_cap, int64_t row_bytes, void* dst, int64_t dst_stride, void* stream);
+
 /* ---- deterministic evaluator ------------------------------------------------------------------ */
 
 /* The deterministic policy/value stub of the parity contract ("visit counts bit-exact ... when both use a fixed

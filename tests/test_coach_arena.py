@@ -115,3 +115,70 @@ def test_batched_arena(backend):
         one, two, dr = arena.playGames(7)
         assert one + two + dr == 7
         assert (one, two, dr) == BatchedArena(ev, num_sims=6, opponent=opp, seed=3, max_turns=10, backend=backend).playGames(7)
+
+
+# ---- Arena against the reference-derived fixtures (tests/golden/make_golden_arena.py) ------------------------------------
+@pytest.mark.parametrize("name", ["vs_greedy", "vs_random"])
+def test_batched_arena_reproduces_the_reference_arena(backend, golden_dir, name):
+    """The live reference's Arena.playGame (Arena.py:38-88) with its MCTSPlayer on the stub net against its GreedyPlayer /
+    RandomPlayer, draws injected, frozen move by move: BatchedArena plays the same games -- every move of both players,
+    every result, the W/L/D totals, with the reference's colour split (i <= num // 2)."""
+    from inflexion_b200.arena_batched import BatchedArena
+    g = np.load(os.path.join(golden_dir, f"arena_{name}.npz"))
+    mode = str(g["mode"])
+    arena = BatchedArena(lambda x: stub_policy_value(x, mode), int(g["sims"]), float(g["cpuct"]), opponent=str(g["opponent"]),
+                         seed=int(g["seed"]), max_turns=int(g["max_turns"]), backend=backend, record=True)
+    totals = arena.playGames(int(g["num"]), shard=False)
+    got = arena.last_actions.T                                  # [games, plies]
+    want = g["actions"]
+    assert got.shape[1] >= want.shape[1]
+    assert np.array_equal(got[:, :want.shape[1]], want) and bool((got[:, want.shape[1]:] == -1).all())
+    assert np.array_equal(arena.last_results, g["result"])
+    assert list(totals) == g["totals"].tolist()
+
+
+@pytest.mark.parametrize("name", ["vs_greedy", "vs_random"])
+def test_object_arena_reproduces_the_reference_arena(backend, golden_dir, name, monkeypatch):
+    """The same fixtures through the drop-in classes a pit.py user touches: Arena.playGames over MCTSPlayer(MCTS(...)),
+    GreedyPlayer / RandomPlayer objects (one game at a time).  RandomPlayer draws with np.random.choice, as the
+    reference's does; the test injects the fixture's draws there."""
+    from oracle.inflexion_mcts import philox4x32
+    g = np.load(os.path.join(golden_dir, f"arena_{name}.npz"))
+    monkeypatch.setattr(backend_mod, "_DEFAULT", backend)
+    seed, mode, num = int(g["seed"]), str(g["mode"]), int(g["num"])
+
+    class Net:
+        def predict(self, planes):
+            pi, v = stub_policy_value(torch.from_numpy(np.ascontiguousarray(planes))[None], mode)
+            return pi.numpy()[0], v.numpy()
+    args = dotdict({"numMCTSSims": int(g["sims"]), "cpuct": float(g["cpuct"])})
+    game = InflexionGame(7, max_turns=int(g["max_turns"]), max_power=6)
+    state = {"game": -1, "ply": 0}
+    played = [[] for _ in range(num)]
+
+    class Spy:
+        def __init__(self, inner, counts_games):
+            self.inner, self.counts_games = inner, counts_games
+
+        def play(self, gm):
+            state["ply"] = gm._curr_turn
+            a = self.inner.play(gm)
+            played[state["game"]].append(int(a))
+            return a
+
+        def reset(self):
+            if self.counts_games:
+                state["game"] += 1
+            return Spy(self.inner.reset(), False)
+    key = ((seed ^ 0x5EED) & 0xFFFFFFFF, ((seed ^ 0x5EED) >> 32) & 0xFFFFFFFF)
+
+    def choice(a, *rest, **kw):
+        a = np.asarray(a)
+        return a[philox4x32((state["game"], state["ply"], 0, 3), key)[0] % len(a)]
+    monkeypatch.setattr(np.random, "choice", choice)
+    opp = GreedyPlayer() if str(g["opponent"]) == "greedy" else RandomPlayer()
+    arena = Arena(Spy(MCTSPlayer(MCTS(Net(), args, seed=seed, backend=backend)), True), Spy(opp, False), game)
+    totals = arena.playGames(num)
+    assert list(totals) == g["totals"].tolist()
+    for i in range(num):
+        assert played[i] == g["actions"][i, :g["plies"][i]].tolist(), i
