@@ -50,21 +50,65 @@ def main():
     examples = coach.selfPlayBatch(a.games * world, seed=1, gather=a.gather, compact=a.compact)   # this rank's games (all with --gather)
     torch.cuda.synchronize()
     t1 = time.time()
-    moves = a.max_turns + 1
     if rank == 0:
-        print(f"self-play: {a.games * world} games x {moves} moves x {a.sims} sims on {world} GPU(s) in {t1 - t0:.1f}s "
-              f"({a.games * world * moves * a.sims / (t1 - t0):.3e} sims/s incl. example expansion); "
-              f"{len(examples)} examples on rank 0", flush=True)
+        print(f"self-play: {a.games * world} games (<= {a.max_turns + 1} moves each) x {a.sims} sims on {world} GPU(s) in {t1 - t0:.1f}s "
+              f"= {a.games * world / (t1 - t0):.1f} games/s incl. the example gather/expansion; {len(examples)} examples on rank 0",
+              flush=True)
+    n_local = torch.tensor([len(examples)], dtype=torch.int64, device="cuda")
+    n_all = [torch.zeros_like(n_local) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(n_all, n_local)
+    else:
+        n_all = [n_local]
     np.random.seed(rank)                                        # every rank draws its own batches
-    hist = nnet.train(examples, verbose=False)                  # gradients all-reduced across ranks
-    w = torch.cat([p.detach().reshape(-1) for p in nnet.nnet.parameters()])
-    if world > 1:                                               # ranks must hold identical weights after training
+    torch.cuda.synchronize()
+    t_tr = time.time()
+    hist = nnet.train(examples, verbose=False)                  # gradients all-reduced across ranks (DDP buckets)
+    torch.cuda.synchronize()
+    t_tr = time.time() - t_tr
+    w = torch.cat([t.detach().reshape(-1).float() for t in nnet.nnet.state_dict().values()])
+    if world > 1:                                               # ranks must hold identical nets after training
         ref = w.clone()
         dist.broadcast(ref, 0)
         assert torch.equal(ref, w), "ranks diverged"
+    steps = a.epochs * int(sum(int(x) for x in n_all) / nnet_mod.args.batch_size)
     if rank == 0:
-        print("train: loss_pi %.3f -> %.3f, loss_v %.3f -> %.3f (weights identical on all ranks)"
-              % (hist[0][0], hist[-1][0], hist[0][1], hist[-1][1]), flush=True)
+        print(f"examples per rank: {[int(x) for x in n_all]} (games end at different moves, so the counts may differ)", flush=True)
+        print("train: %d steps in %.1fs (%.2f ms/step, global batch %d = %d per rank); loss_pi %.3f -> %.3f, loss_v %.3f -> %.3f; "
+              "parameters and BatchNorm buffers identical on all ranks"
+              % (steps, t_tr, 1e3 * t_tr / max(steps, 1), nnet_mod.args.batch_size, nnet_mod.args.batch_size // world,
+                 hist[0][0], hist[-1][0], hist[0][1], hist[-1][1]), flush=True)
+    if world > 1:
+        # how much of a training step is exposed all-reduce: the same step with and without gradient synchronisation
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        ddp = DDP(nnet.nnet, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True, bucket_cap_mb=8)
+        opt = torch.optim.Adam(nnet.nnet.parameters())
+        per = nnet_mod.args.batch_size // world
+        x = torch.randint(0, 2, (per, 4, 7, 7), device="cuda").float()
+        tp = torch.full((per, 343), 1.0 / 343, device="cuda")
+        tv = torch.zeros(per, device="cuda")
+        nnet.nnet.train()
+
+        def run(sync, n=30):
+            torch.cuda.synchronize(); dist.barrier(); t = time.time()
+            for _ in range(n):
+                ctx = ddp.no_sync() if not sync else torch.autograd.profiler.record_function("sync")
+                with ctx:
+                    lp, v = ddp(x)
+                    loss = nnet.loss_pi(tp, lp) + nnet.loss_v(tv, v)
+                    opt.zero_grad(set_to_none=False)
+                    loss.backward()
+                opt.step()
+            torch.cuda.synchronize(); dist.barrier()
+            return (time.time() - t) / n
+        run(True, 5); run(False, 5)
+        t_sync, t_nosync = run(True), run(False)
+        nnet.nnet.eval()
+        nnet.weights_changed()
+        if rank == 0:
+            print("all-reduce share of a train step: %.2f ms with the bucketed all-reduce overlapped with backward vs %.2f ms "
+                  "without gradient synchronisation -> %.1f %% exposed (50 MB of fp32 gradients per step over NVLink)"
+                  % (1e3 * t_sync, 1e3 * t_nosync, 100 * max(t_sync - t_nosync, 0) / t_sync), flush=True)
     for opp in ("random", "greedy"):
         t2 = time.time()
         one, two, dr = BatchedArena(nnet.predict_head, a.sims, opponent=opp, seed=2, max_turns=a.max_turns,
