@@ -57,6 +57,7 @@ PROTOTYPES = {
     "ifx_mcts_reset_games": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_set_roots": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_wave": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ifx_mcts_wave_part": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_root_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ifx_mcts_sample_actions": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
     "ifx_mcts_advance": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -153,17 +153,17 @@ __global__ void tree_sym_lut_kernel() {                      // <<<126, 64>>>: o
 template <bool DBG>
 __global__ void __launch_bounds__(TREE_BLOCK, IFX_WAVE_MIN_BLOCKS)
 tree_wave_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_stride, const float* __restrict__ nn_v,
-                 float* __restrict__ nn_in) {
+                 float* __restrict__ nn_in, int g_first, int g_end) {
   __shared__ ExpandScratch scratch[TREE_WARPS];
   __shared__ RootMirror mirror[TREE_WARPS];
-  const int w = threadIdx.x >> 5, g = blockIdx.x * TREE_WARPS + w;
-  if (g < P.G) tree_wave_game<DBG>(P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch[w], &mirror[w]);
+  const int w = threadIdx.x >> 5, g = g_first + blockIdx.x * TREE_WARPS + w;
+  if (g < g_end) tree_wave_game<DBG>(P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch[w], &mirror[w]);
 }
 
 __global__ void __launch_bounds__(TREE_BLOCK)
-tree_noise_kernel(TreeParams P) {
-  const int g = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
-  if (g < P.G) body_root_noise(P, g);
+tree_noise_kernel(TreeParams P, int g_first, int g_end) {
+  const int g = g_first + blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (g < g_end) body_root_noise(P, g);
 }
 __global__ void __launch_bounds__(TREE_BLOCK)
 tree_reset_kernel(TreeParams P, const ifx_state* __restrict__ roots, const int32_t* __restrict__ which) {
@@ -375,17 +375,26 @@ int ifx_mcts_set_roots(ifx_mcts* m, const ifx_state* roots, void* stream) {
 }
 
 int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const float* nn_v, float* nn_in, void* stream) {
+  return m ? ifx_mcts_wave_part(m, 0, m->P.G, nn_pi, pi_stride, nn_v, nn_in, stream) : IFX_E_ARG;
+}
+
+int ifx_mcts_wave_part(ifx_mcts* m, int32_t first_game, int32_t n_games, const float* nn_pi, int64_t pi_stride,
+                       const float* nn_v, float* nn_in, void* stream) {
   if (!m || !nn_pi || !nn_in || pi_stride < IFX_ACTIONS) return IFX_E_ARG;
+  if (first_game < 0 || n_games < 0 || first_game + n_games > m->P.G) return IFX_E_ARG;
+  if (n_games == 0) return IFX_OK;
+  const int g_end = first_game + n_games;
   if (m->P.logits == 2) {                  // nn_pi = binary16 head rows: 343 logits + value, 8-byte aligned rows
     if (pi_stride < 344 || (pi_stride & 3) || ((uintptr_t)nn_pi & 7)) return IFX_E_ARG;
   } else if (!nn_v) return IFX_E_ARG;
 #ifdef IFX_HOSTSIM
   static ExpandScratch scratch;
   static RootMirror mirror;
-  for (int g = 0; g < m->P.G; ++g) tree_wave_game<false>(m->P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch, &mirror);
-  if (m->P.dir_eps > 0.0f) for (int g = 0; g < m->P.G; ++g) body_root_noise(m->P, g);
+  for (int g = first_game; g < g_end; ++g) tree_wave_game<false>(m->P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch, &mirror);
+  if (m->P.dir_eps > 0.0f) for (int g = first_game; g < g_end; ++g) body_root_noise(m->P, g);
   return ifx_after_launch();
 #else
+  const unsigned grid = (unsigned)((n_games + TREE_WARPS - 1) / TREE_WARPS);
   const bool timed = m->timing && m->n_timed < IFX_TIMING_RING;
   if (timed) {
     while (m->ev_made <= m->n_timed) {
@@ -395,12 +404,12 @@ int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const floa
     cudaEventRecord(m->ev[m->n_timed][0], (cudaStream_t)stream);
   }
   if (m->P.debug)    // per-warp %globaltimer stamps (tools/trace_wave.py): a separate instantiation, so the product kernel carries none of it
-    tree_wave_kernel<true><<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
+    tree_wave_kernel<true><<<grid, TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in, first_game, g_end);
   else
-    tree_wave_kernel<false><<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in);
+    tree_wave_kernel<false><<<grid, TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in, first_game, g_end);
   if (timed) { cudaEventRecord(m->ev[m->n_timed][1], (cudaStream_t)stream); m->n_timed += 1; }
   if (m->P.dir_eps > 0.0f) {               // noise mode only: one more (tiny) launch per wave
-    tree_noise_kernel<<<TREE_GRID(m->P), TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P);
+    tree_noise_kernel<<<grid, TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, first_game, g_end);
     ifx_count_launches(1);
   }
   return ifx_after_launch();

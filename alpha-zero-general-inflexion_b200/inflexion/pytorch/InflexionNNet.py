@@ -93,7 +93,7 @@ class FoldedInference:
             self.w1p_t = w1p.to(dtype).contiguous().t()               # [64,512] view of the row-major [512,64] weights
             from ... import _capi
             self._dll = _capi.lib()
-            self._cols = None
+            self._cols = {}
         self.convs = []
         for conv, bn, pad in ((net.conv2, net.bn2, 1), (net.conv3, net.bn3, 0), (net.conv4, net.bn4, 0)):
             w, b = _fold(conv.weight, conv.bias, bn)
@@ -120,11 +120,16 @@ class FoldedInference:
         """conv1 + BN + ReLU as im2col (our kernel) + one GEMM with a fused bias+ReLU epilogue (cuBLASLt)."""
         n = x.shape[0]
         x = x.contiguous()
-        if self._cols is None or self._cols.shape[0] != n * 49:
-            self._cols = torch.empty((n * 49, 64), dtype=self.dtype, device=x.device)
-        _capi_check(self._dll.ifx_net_im2col3x3(x.data_ptr(), n, self._cols.data_ptr(),
+        # one im2col buffer per input buffer: two halves of a batch may be evaluated concurrently on two streams
+        key = (x.data_ptr(), n)
+        cols = self._cols.get(key)
+        if cols is None:
+            if len(self._cols) > 16:
+                self._cols.clear()
+            cols = self._cols[key] = torch.empty((n * 49, 64), dtype=self.dtype, device=x.device)
+        _capi_check(self._dll.ifx_net_im2col3x3(x.data_ptr(), n, cols.data_ptr(),
                                                 torch.cuda.current_stream(x.device).cuda_stream), self._dll)
-        s = torch._addmm_activation(self.b1, self._cols, self.w1p_t, use_gelu=False)      # [n*49, 512] = NHWC
+        s = torch._addmm_activation(self.b1, cols, self.w1p_t, use_gelu=False)            # [n*49, 512] = NHWC
         return s.view(n, 7, 7, -1).permute(0, 3, 1, 2)                       # NCHW view of channels-last memory
 
     def _trunk(self, x: torch.Tensor):

@@ -145,13 +145,15 @@ class BatchedMCTS:
         self.be.check(self.be.dll.ifx_mcts_set_params(self._h, self.num_sims, float(np.float32(cpuct))))
 
     # ---- search ---------------------------------------------------------------------------------
-    def wave(self) -> None:
+    def wave(self, part: tuple[int, int] | None = None) -> None:
+        """One lock-step wave over all games, or over the games ``part = (first, count)`` only (ifx_mcts_wave_part)."""
+        first, count = part if part is not None else (0, self.n_games)
         if self.fused_head:
-            self.be.check(self.be.dll.ifx_mcts_wave(self._h, self.nn_head.data_ptr(), self.nn_head.stride(0), None,
-                                                    self.nn_in.data_ptr(), self.be.stream()))
+            self.be.check(self.be.dll.ifx_mcts_wave_part(self._h, first, count, self.nn_head.data_ptr(), self.nn_head.stride(0),
+                                                         None, self.nn_in.data_ptr(), self.be.stream()))
         else:
-            self.be.check(self.be.dll.ifx_mcts_wave(self._h, self.nn_pi.data_ptr(), self.nn_pi.stride(0),
-                                                    self.nn_v.data_ptr(), self.nn_in.data_ptr(), self.be.stream()))
+            self.be.check(self.be.dll.ifx_mcts_wave_part(self._h, first, count, self.nn_pi.data_ptr(), self.nn_pi.stride(0),
+                                                         self.nn_v.data_ptr(), self.nn_in.data_ptr(), self.be.stream()))
         self.waves_run += 1
 
     # ---- leaf gather (north_star kernel 3) -----------------------------------------------------------
@@ -202,8 +204,22 @@ class BatchedMCTS:
                             (344 if padded else 343) * 4)
             self._move_rows(dll.ifx_gather_scatter_rows, b["v"], self.nn_v, rows, 4)
 
-    def feed(self, evaluate) -> None:
-        """One net evaluation of the pending leaves into the buffers the next wave reads."""
+    def feed(self, evaluate, part: tuple[int, int] | None = None) -> None:
+        """One net evaluation of the pending leaves into the buffers the next wave reads (``part``: of the games
+        (first, count) only -- dense mode)."""
+        if part is not None:
+            a, b = part[0], part[0] + part[1]
+            self.rows_evaluated += part[1]
+            if self.fused_head:
+                evaluate(self.nn_in[a:b], self.nn_head[a:b])
+            else:
+                pi, v = evaluate(self.nn_in[a:b])
+                if pi.data_ptr() != self.nn_pi[a:b].data_ptr():
+                    self.nn_pi[a:b].copy_(pi)
+                if v.data_ptr() != self.nn_v[a:b].data_ptr():
+                    self.nn_v[a:b].copy_(v.reshape(-1))
+            self.evals_run += 1
+            return
         self.rows_evaluated += self.rows_active
         if self.rows_active < self.n_games:
             self._feed_packed(evaluate, self.rows_active)

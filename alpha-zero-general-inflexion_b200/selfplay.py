@@ -27,12 +27,16 @@ class SelfPlayEngine:
                  max_turns: int = 343, game_id_base: int = 0, nodes_per_game: int | None = None,
                  record: bool = True, use_graph: bool | None = None, backend: Backend | None = None,
                  fused_head: bool = False, auto_restart: bool = False, restart_stride: int | None = None,
-                 record_moves: int | None = None, dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.0):
+                 record_moves: int | None = None, dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.0,
+                 streams: int = 1):
         """evaluate(nn_in f32 [G,4,7,7]) -> (pi f32 [G,343], v f32 [G]) on the device (e.g. nnet.predict_batch); with
         ``fused_head`` it is evaluate(nn_in, out f16 [G,344]) writing the raw head output (e.g. nnet.predict_head) and
         the tree kernel does the softmax / tanh.  ``auto_restart``: a game that ends starts its next episode at once
         (continuous self-play, Coach.py:108-112) with RNG stream id + ``restart_stride`` (default: n_games; pass the
-        global game count when several ranks play)."""
+        global game count when several ranks play).  ``streams`` = 2: inside the captured move the games are searched as
+        two halves on two streams, so the tree wave of one half runs while the net evaluates the other half (the
+        latency-bound wave fills issue slots the tensor-bound convolutions leave idle); results are identical -- games
+        are independent.  Used with CUDA graphs and a dense batch only."""
         self.be = backend or default_backend()
         self.G, self.num_sims, self.temp_threshold = int(n_games), int(num_sims), int(temp_threshold)
         self.max_turns, self.game_id_base = int(max_turns), int(game_id_base)
@@ -55,6 +59,8 @@ class SelfPlayEngine:
         # fixed sets of episodes (no auto_restart) thin out as games end: the net then runs on the live games only
         # (BatchedMCTS.plan_rows: one host read per move, a captured graph per batch size)
         self.pack = not self.auto_restart
+        self.streams = 2 if (int(streams) == 2 and self.G >= 2) else 1
+        self._side = None
         self.move = 0
         self.my_launches = 0                                      # kernels of libifx_b200 launched (bench evidence)
         self.extra_launches_per_search = 0                        # library kernels inside `evaluate` (the stub evaluator)
@@ -80,18 +86,39 @@ class SelfPlayEngine:
         s.wait_stream(torch.cuda.current_stream(self.be.device))
         with torch.cuda.stream(s):
             rows = self.mcts.rows_active
-            for _ in range(2):                                   # warm the allocator / cuDNN heuristics (results unused)
-                if self.mcts.fused_head:
-                    self.evaluate(self.mcts.nn_in[:rows], torch.empty_like(self.mcts.nn_head[:rows]))
-                else:
-                    self.evaluate(self.mcts.nn_in[:rows])
+            two = self.streams == 2 and rows == self.G
+            half = self.G // 2
+            # warm the allocator / cuDNN heuristics for every batch shape the capture will see (results unused)
+            shapes = ((0, half), (half, self.G)) if two else ((0, rows),)
+            for _ in range(2):
+                for a, b in shapes:
+                    if self.mcts.fused_head:
+                        self.evaluate(self.mcts.nn_in[a:b], torch.empty_like(self.mcts.nn_head[a:b]))
+                    else:
+                        self.evaluate(self.mcts.nn_in[a:b])
         torch.cuda.current_stream(self.be.device).wait_stream(s)
         torch.cuda.synchronize(self.be.device)
         graph = torch.cuda.CUDAGraph()
+        two = self.streams == 2 and self.mcts.rows_active == self.G
+        if two and self._side is None:
+            self._side = torch.cuda.Stream(device=self.be.device)
         with torch.cuda.graph(graph):
-            for _ in range(self.mcts.waves_per_search - 1):
-                self._wave_and_net()
-            self.mcts.wave()
+            if not two:
+                for _ in range(self.mcts.waves_per_search - 1):
+                    self._wave_and_net()
+                self.mcts.wave()
+            else:                                                # two independent chains: (wave, net)* for each half
+                main = torch.cuda.current_stream(self.be.device)
+                half = self.G // 2
+                parts = ((0, half), (half, self.G - half))
+                self._side.wait_stream(main)
+                for stream, part in ((self._side, parts[1]), (main, parts[0])):
+                    with torch.cuda.stream(stream):
+                        for _ in range(self.mcts.waves_per_search - 1):
+                            self.mcts.wave(part)
+                            self.mcts.feed(self.evaluate, part)
+                        self.mcts.wave(part)
+                main.wait_stream(self._side)
         self._graphs[self.mcts.rows_active] = graph
 
     def search(self, wave_timer=None) -> None:

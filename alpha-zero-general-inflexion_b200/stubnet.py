@@ -54,11 +54,15 @@ def stub_kernel_evaluator(mcts, mode: str = "float"):
     assert not mcts.fused_head
 
     def evaluate(nn_in):
-        be.check(be.dll.ifx_stub_policy_value(nn_in.data_ptr(), nn_in.shape[0], coef.data_ptr(), int(mode == "dyadic"),
-                                              mcts.nn_pi.data_ptr(), mcts.nn_pi.stride(0), mcts.nn_v.data_ptr(),
-                                              be.stream()))
-        n = nn_in.shape[0]                                    # (a packed batch is smaller than the game count: views of its rows)
-        return (mcts.nn_pi, mcts.nn_v) if n == mcts.n_games else (mcts.nn_pi[:n], mcts.nn_v[:n])
+        # rows of the search's own input buffer (all of it, or one half on its own stream) are answered in the same rows
+        # of nn_pi / nn_v; any other batch (a packed one) in rows 0..n-1, which the caller then scatters
+        n = nn_in.shape[0]
+        off = nn_in.data_ptr() - mcts.nn_in.data_ptr()
+        r0 = off // 784 if (0 <= off < mcts.n_games * 784 and off % 784 == 0) else 0
+        pi, v = mcts.nn_pi[r0:r0 + n], mcts.nn_v[r0:r0 + n]
+        be.check(be.dll.ifx_stub_policy_value(nn_in.data_ptr(), n, coef.data_ptr(), int(mode == "dyadic"),
+                                              pi.data_ptr(), mcts.nn_pi.stride(0), v.data_ptr(), be.stream()))
+        return (mcts.nn_pi, mcts.nn_v) if n == mcts.n_games else (pi, v)
     return evaluate
 
 

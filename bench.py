@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--nodes", type=int, default=None, help="node pool slots per game (default: mcts_batched.default_pool_size)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
+                    help="2 = search the games as two halves on two streams inside the captured move (tree wave of one half "
+                         "under the net forward of the other)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra-rooflines", action="store_true",
                     help="skip the stub-net tree roofline and the rules-kernel roofline appended to the default N=1 line")
@@ -337,6 +340,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")         # (keeps NCCL's version banner off stdout: one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     be = Backend.cuda(local)
     peaks = {}
@@ -360,7 +364,7 @@ def run_ours(a):
 
     eng = SelfPlayEngine(a.games, a.sims, evaluate, cpuct=1.0, temp_threshold=30, seed=2023, max_turns=343,
                          game_id_base=rank * a.games, record=True, backend=be, fused_head=fused, nodes_per_game=a.nodes,
-                         auto_restart=True, restart_stride=world * a.games)
+                         auto_restart=True, restart_stride=world * a.games, streams=a.streams)
     if a.net == "stub":                                    # deterministic stub evaluator, one kernel per wave (csrc/ifx_stub.cu)
         eng.evaluate = stub_kernel_evaluator(eng.mcts)
     eng.extra_launches_per_search = a.sims                 # per net evaluation one kernel of ours: the stub, or conv1's im2col

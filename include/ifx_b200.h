@@ -208,6 +208,12 @@ IFX_API int ifx_mcts_set_roots(ifx_mcts* m, const ifx_state* roots, void* stream
 IFX_API int ifx_mcts_wave(ifx_mcts* m, const float* nn_pi, int64_t pi_stride, const float* nn_v, float* nn_in,
                           void* stream);
 
+/* The same wave for the games [first_game, first_game + n_games) only; row g of nn_pi / nn_v / nn_in still belongs to
+ * game g.  Games are independent, so disjoint parts may run on different streams: with two halves, the tree wave of one
+ * half fills the issue slots the other half's net forward leaves idle (SelfPlayEngine(streams=2)). */
+IFX_API int ifx_mcts_wave_part(ifx_mcts* m, int32_t first_game, int32_t n_games, const float* nn_pi, int64_t pi_stride,
+                               const float* nn_v, float* nn_in, void* stream);
+
 /* Root tables after the search (getActionProb, MCTS.py:48-49): any output may be NULL.
  * counts int32 [G][343]; q32 float [G][343]; q64 double [G][343]; qkind uint8 [G][343] (1 = float32 kind,
  * 0 = Python-float kind); ns int32 [G]. */

@@ -36,7 +36,7 @@ def test_gpu_arm_control_flow_and_json_line(monkeypatch, capsys):
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="ours", games=6, sims=5, net="stub", workload="selfplay",
                                  states=0, nodes=None, cpu_baseline_seconds=0.0, no_cpu_baseline=True, no_e2e=False,
-                                 no_extra_rooflines=True)
+                                 no_extra_rooflines=True, streams=1)
     bench.run_ours(args)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
