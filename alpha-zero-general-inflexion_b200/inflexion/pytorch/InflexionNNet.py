@@ -84,13 +84,13 @@ class FoldedInference:
         w1, b1 = _fold(net.conv1.weight, net.conv1.bias, net.bn1)
         self.w1 = w1.to(self.first_dtype).contiguous(memory_format=torch.channels_last)
         self.b1 = b1.to(self.first_dtype)
-        # conv1 as a GEMM over im2col rows written by libifx_b200 (csrc/ifx_net.cu): [B*49, 64] x [64, 512], taps
-        # c*9 + ky*3 + kx zero-padded from 36 to 64.  CUDA + fp16 only; elsewhere conv1 stays a convolution.
+        # conv1 as a GEMM over im2col rows written by libifx_b200 (csrc/ifx_net.cu): [B*49, 48] x [48, 512], taps
+        # c*9 + ky*3 + kx zero-padded from 36 to 48.  CUDA + fp16 only; elsewhere conv1 stays a convolution.
         self.gemm_conv1 = dev.type == "cuda" and dtype == torch.float16
         if self.gemm_conv1:
-            w1p = torch.zeros((w1.shape[0], 64), dtype=torch.float32, device=dev)
+            w1p = torch.zeros((w1.shape[0], 48), dtype=torch.float32, device=dev)
             w1p[:, :36] = w1.reshape(w1.shape[0], 36)
-            self.w1p_t = w1p.to(dtype).contiguous().t()               # [64,512] view of the row-major [512,64] weights
+            self.w1p_t = w1p.to(dtype).contiguous().t()               # [48,512] view of the row-major [512,48] weights
             from ... import _capi
             self._dll = _capi.lib()
             self._cols = {}
@@ -126,7 +126,7 @@ class FoldedInference:
         if cols is None:
             if len(self._cols) > 16:
                 self._cols.clear()
-            cols = self._cols[key] = torch.empty((n * 49, 64), dtype=self.dtype, device=x.device)
+            cols = self._cols[key] = torch.empty((n * 49, 48), dtype=self.dtype, device=x.device)
         _capi_check(self._dll.ifx_net_im2col3x3(x.data_ptr(), n, cols.data_ptr(),
                                                 torch.cuda.current_stream(x.device).cuda_stream), self._dll)
         s = torch._addmm_activation(self.b1, cols, self.w1p_t, use_gelu=False)            # [n*49, 512] = NHWC

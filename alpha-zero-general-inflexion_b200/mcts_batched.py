@@ -141,6 +141,10 @@ class BatchedMCTS:
         return self.num_sims + 1 + (1 if self.dirichlet_eps > 0 else 0)
 
     def set_params(self, num_sims: int, cpuct) -> None:
+        """args.numMCTSSims / args.cpuct for the searches that follow.  A CUDA graph captured earlier has the old values
+        baked into its kernel arguments: ``params_version`` changes so that owners of such graphs (SelfPlayEngine)
+        re-capture."""
+        self.params_version = getattr(self, "params_version", 0) + 1
         self.num_sims = int(num_sims)
         self.be.check(self.be.dll.ifx_mcts_set_params(self._h, self.num_sims, float(np.float32(cpuct))))
 

@@ -130,6 +130,9 @@ class SelfPlayEngine:
         if self.pack and self.mcts.plan_rows() and self.mcts.live_count == 0:
             return                                               # every game is over: nothing to search
         if self.use_graph and wave_timer is None:
+            if getattr(self.mcts, "params_version", 0) != getattr(self, "_graphs_version", 0):
+                self._graphs.clear()                             # set_params since the capture: the graphs hold the old values
+                self._graphs_version = getattr(self.mcts, "params_version", 0)
             if self.mcts.rows_active not in self._graphs:
                 self._capture()
             self._graphs[self.mcts.rows_active].replay()

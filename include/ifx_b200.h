@@ -174,6 +174,8 @@ IFX_API size_t ifx_mcts_workspace_bytes(const ifx_mcts_config* cfg);
 /* MCTS.__init__ (MCTS.py:21-31).  `workspace` is a device buffer of ifx_mcts_workspace_bytes, 256-B aligned. */
 IFX_API int ifx_mcts_create(const ifx_mcts_config* cfg, void* workspace, size_t workspace_bytes, ifx_mcts** out);
 IFX_API void ifx_mcts_destroy(ifx_mcts* m);
+/* args.numMCTSSims (< 2^17) and float32(args.cpuct) for the waves launched from now on.  The values travel as kernel
+ * arguments: a CUDA graph captured before the call keeps the old ones and must be captured again. */
 IFX_API int ifx_mcts_set_params(ifx_mcts* m, int32_t num_sims, float cpuct);
 /* CUDA-event timing of the wave kernel on its launching stream: while enabled, every ifx_mcts_wave (outside
  * graph capture) is bracketed by an event pair recorded inside the call; ifx_mcts_wave_time synchronises on them,
@@ -272,10 +274,10 @@ IFX_API int ifx_stub_policy_value(const float* nn_in, int64_t n, const int64_t* 
 /* ---- input stage of the policy/value net ------------------------------------------------------- */
 
 /* im2col of the net input for conv1 (3x3, pad 1; inflexion/pytorch/InflexionNNet.py:24,41 of the reference):
- * planes float32 [n][4][7][7] -> out binary16 [n*49][64], row = position*49 + y*7 + x, column = c*9 + ky*3 + kx for
- * the 36 taps (zero outside the board), columns 36..63 zero.  conv1 + BN + ReLU then is ONE tensor-core GEMM
- * [n*49,64] x [64,512] with a bias+ReLU epilogue, and its output is the channels-last activation conv2 reads
- * (NNetWrapper.predict_batch / predict_head, the batched form of NNet.py:78-94).  GPU build only. */
+ * planes float32 [n][4][7][7] -> out binary16 [n*49][48] (16-byte aligned), row = position*49 + y*7 + x, column =
+ * c*9 + ky*3 + kx for the 36 taps (zero outside the board), columns 36..47 zero.  conv1 + BN + ReLU then is ONE
+ * tensor-core GEMM [n*49,48] x [48,512] with a bias+ReLU epilogue, and its output is the channels-last activation
+ * conv2 reads (NNetWrapper.predict_batch / predict_head, the batched form of NNet.py:78-94).  GPU build only. */
 IFX_API int ifx_net_im2col3x3(const float* planes, int64_t n, void* out, void* stream);
 
 #ifdef __cplusplus

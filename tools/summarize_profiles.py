@@ -64,20 +64,20 @@ def traffic_of(rep):
             "ncu_duration_" + units[i_t]: sum(dur) / len(dur), "source": os.path.basename(rep)}
 
 g = os.path.join(ROOT, "gpurun_out")
-launch_list(os.path.join(g, "launches_default_r1.csv"), os.path.join(OUT, f"{tag}_launches_bench_default.txt"),
+launch_list(os.path.join(g, f"launches_default_{tag}.csv"), os.path.join(OUT, f"{tag}_launches_bench_default.txt"),
             "bench.py --steps 1 --warmup 3 (default net, 4096 games x 100 sims): per-kernel device time")
-full_summary(os.path.join(g, "tree_default_r1.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_tree_wave_kernel.txt"),
+full_summary(os.path.join(g, f"tree_default_{tag}.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_tree_wave_kernel.txt"),
              "tree_wave_kernel inside bench.py (default net, 4096 games x 100 sims/move)")
-full_summary(os.path.join(g, "tree_stub_r1.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_tree_wave_kernel_stub.txt"),
+full_summary(os.path.join(g, f"tree_stub_{tag}.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_tree_wave_kernel_stub.txt"),
              "tree_wave_kernel inside bench.py --net stub (tree + rules only, 4096 games x 100 sims/move)")
-full_summary(os.path.join(g, "rules_r1.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_rules_mask_step_kernel.txt"),
+full_summary(os.path.join(g, f"rules_{tag}.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_rules_mask_step_kernel.txt"),
              "rules_mask_step_kernel, bench.py --workload rules (4 Mi states per launch)")
-traffic = {"tree_wave_kernel": {"default": traffic_of(os.path.join(g, "tree_default_r1.ncu-rep")),
-                                "stub": traffic_of(os.path.join(g, "tree_stub_r1.ncu-rep"))},
-           "rules_mask_step_kernel": {"rules": traffic_of(os.path.join(g, "rules_r1.ncu-rep"))}}
+traffic = {"tree_wave_kernel": {"default": traffic_of(os.path.join(g, f"tree_default_{tag}.ncu-rep")),
+                                "stub": traffic_of(os.path.join(g, f"tree_stub_{tag}.ncu-rep"))},
+           "rules_mask_step_kernel": {"rules": traffic_of(os.path.join(g, f"rules_{tag}.ncu-rep"))}}
 json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
-rep = os.path.join(g, "net_convs_r1.ncu-rep")
+rep = os.path.join(g, f"net_convs_{tag}.ncu-rep")
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.split("\n")))
@@ -88,17 +88,17 @@ if os.path.exists(rep):
             "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active"]
     with open(os.path.join(OUT, f"{tag}_ncu_net_convolutions.txt"), "w") as f:
         f.write("# the policy/value net's 512-channel convolutions inside bench.py (cuDNN/CUTLASS library kernels, fp16 in / fp32 accumulate)\n"
-                "# source: ncu --set full --clock-control none (net_convs_r1.ncu-rep), one column per profiled launch\n")
+                "# source: ncu --set full --clock-control none (net_convs_{tag}.ncu-rep), one column per profiled launch\n")
         for w in want:
             if w in hdr:
                 i = hdr.index(w)
                 f.write(f"{w} [{units[i]}]: {' | '.join(r[i][:60] for r in rows[2:] if len(r) > i)}\n")
     print(open(os.path.join(OUT, f"{tag}_ncu_net_convolutions.txt")).read())
 for name in ("bench_default", "bench_stub", "bench_rules", "bench_reference", "bench_sims200"):
-    src = os.path.join(g, name + ".json")
+    src = os.path.join(g, f"{tag}_{name}.json")
     if os.path.exists(src):
         open(os.path.join(OUT, f"{tag}_{name}.json"), "w").write(open(src).read())
 for name in ("trace_default", "trace_stub"):
-    src = os.path.join(g, name + ".log")
+    src = os.path.join(g, f"{tag}_{name}.log")
     if os.path.exists(src):
         open(os.path.join(OUT, f"{tag}_{name}.txt"), "w").write("# tools/trace_wave.py 4096 " + name.split("_")[1] + ": per-warp %globaltimer phases of the wave kernel\n" + open(src).read())
