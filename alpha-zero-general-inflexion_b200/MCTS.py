@@ -49,11 +49,12 @@ class MCTS:
     def _evaluate(self, nn_in: torch.Tensor):
         if hasattr(self.nnet, "predict_batch") and getattr(self.nnet, "device", nn_in.device) == nn_in.device:
             return self.nnet.predict_batch(nn_in)
-        planes = nn_in[0].cpu().numpy().astype(np.int64)                  # what the reference hands to predict
-        pi, v = self.nnet.predict(planes)
-        pi = torch.as_tensor(np.asarray(pi, dtype=np.float32)).reshape(1, -1).to(nn_in.device)
-        v = torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(1).to(nn_in.device)
-        return pi, v
+        pis, vs = [], []
+        for row in nn_in.cpu().numpy().astype(np.int64):                  # what the reference hands to predict
+            pi, v = self.nnet.predict(row)
+            pis.append(np.asarray(pi, dtype=np.float32).reshape(-1))
+            vs.append(np.asarray(v, dtype=np.float32).reshape(-1)[0])
+        return (torch.as_tensor(np.stack(pis)).to(nn_in.device), torch.as_tensor(np.asarray(vs, dtype=np.float32)).to(nn_in.device))
 
     def _install_root(self, game) -> None:
         sims, cpuct = int(self.args.numMCTSSims), self.args.cpuct
@@ -62,7 +63,10 @@ class MCTS:
         if self._tree is None:
             self._tree = BatchedMCTS(1, sims, cpuct, seed=self._seed, backend=self._backend,
                                      nodes_per_game=min(16383, max(4096, 16 * sims)),
-                                     terminal_sims_per_wave=0)   # one game: fewest launches, no tail to bound
+                                     terminal_sims_per_wave=0,   # one game: fewest launches, no tail to bound
+                                     # args.leavesPerWave (not in the reference; default 1 = its sequential search): K > 1
+                                     # searches leaf-parallel with virtual loss -- batch-K net calls instead of batch-1
+                                     leaves_per_wave=int(dict(self.args).get("leavesPerWave", 1)))
             self._tree.reset(state)
         else:
             self._tree.set_params(sims, cpuct)

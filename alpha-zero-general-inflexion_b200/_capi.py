@@ -20,7 +20,7 @@ class MctsConfig(C.Structure):
     _fields_ = [("n_games", c_int32), ("nodes_per_game", c_int32), ("hash_per_game", c_int32),
                 ("max_depth", c_int32), ("num_sims", c_int32), ("cpuct", c_float), ("seed", c_uint64),
                 ("policy_is_logits", c_int32), ("terminal_sims_per_wave", c_int32),
-                ("dirichlet_alpha", c_float), ("dirichlet_eps", c_float)]
+                ("dirichlet_alpha", c_float), ("dirichlet_eps", c_float), ("leaves_per_wave", c_int32)]
 
 
 class MctsLayout(C.Structure):

@@ -130,6 +130,8 @@ struct TreeParams {
   uint8_t* sym;         // [G][sym_cap][64]  source cell of every destination cell under the random_symmetry of simulation i of
                         // the CURRENT move (filled when the move starts); byte 63 of a row = the symmetry code
   int32_t G, C, H, maxd, path_stride, sym_cap, num_sims, logits, term_budget;
+  int32_t vl_mode;            // 1: waves run the leaf-parallel kernel (also for K = 1: a test hook, leaves_per_wave = -1)
+  int32_t leaves_per_wave;    // 1: the reference's sequential search; K > 1: leaf-parallel mode (ifx_tree_vl.cuh), K leaf / path areas per game
   float dir_alpha, dir_eps;   // optional Dirichlet root noise (eps = 0: off = the reference's behaviour)
   uint64_t* debug;      // optional [G][8]: ns stamps {start, loads done, expanded, backed up, first level done, end}, depth, probes
   float cpuct;

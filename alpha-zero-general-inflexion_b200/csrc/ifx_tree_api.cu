@@ -1,5 +1,6 @@
 // Tree kernels (one warp per game) and the ifx_mcts_* C ABI.  See include/ifx_b200.h for the contract.
 #include "ifx_tree.cuh"
+#include "ifx_tree_vl.cuh"
 #include "ifx_host.cuh"
 #include <new>
 
@@ -21,6 +22,7 @@ struct ifx_mcts {
 
 static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 static int32_t sym_cap_of(int32_t num_sims) { const int32_t n = num_sims > 128 ? num_sims : 128; return (n + 31) / 32 * 32; }
+static int32_t leaves_of(const ifx_mcts_config* c) { return c->leaves_per_wave > 1 ? c->leaves_per_wave : 1; }
 static int32_t path_stride_of(int32_t max_depth) { return (max_depth + IFX_PATH_CHUNK - 1) / IFX_PATH_CHUNK * IFX_PATH_CHUNK; }
 
 static int check_cfg(const ifx_mcts_config* c) {
@@ -32,6 +34,8 @@ static int check_cfg(const ifx_mcts_config* c) {
   if (c->policy_is_logits != 0 && c->policy_is_logits != 2) return IFX_E_ARG;
   if (c->terminal_sims_per_wave < 0) return IFX_E_ARG;
   if (c->dirichlet_eps < 0.0f || c->dirichlet_eps > 1.0f || (c->dirichlet_eps > 0.0f && !(c->dirichlet_alpha > 0.0f))) return IFX_E_ARG;
+  if (c->leaves_per_wave < -1 || c->leaves_per_wave > IFX_VL_MAX_LEAVES) return IFX_E_ARG;
+  if (c->leaves_per_wave > 1 && c->dirichlet_eps > 0.0f) return IFX_E_ARG;      // (root noise: sequential mode only)
   return IFX_OK;
 }
 
@@ -160,6 +164,16 @@ tree_wave_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_strid
   if (g < g_end) tree_wave_game<DBG>(P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch[w], &mirror[w]);
 }
 
+// leaf-parallel mode (performance mode, ifx_tree_vl.cuh): one warp per game as well, no register ceiling to meet
+__global__ void __launch_bounds__(32)
+tree_wave_vl_kernel(TreeParams P, const float* __restrict__ nn_pi, int64_t pi_stride, const float* __restrict__ nn_v,
+                    float* __restrict__ nn_in, int g_first, int g_end) {
+  __shared__ ExpandScratch scratch;
+  __shared__ VlScratch vl;
+  const int g = g_first + blockIdx.x;
+  if (g < g_end) tree_wave_game_vl(P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch, &vl);
+}
+
 __global__ void __launch_bounds__(TREE_BLOCK)
 tree_noise_kernel(TreeParams P, int g_first, int g_end) {
   const int g = g_first + blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
@@ -264,9 +278,9 @@ int ifx_mcts_get_layout(const ifx_mcts_config* c, ifx_mcts_layout* L) {
   L->hash = off;       off = align256(off + G * H * 16);
   L->free_stack = off; off = align256(off + G * C * 2);
   L->per_game = off;   off = align256(off + G * (int64_t)sizeof(IfxGame));
-  L->path = off;       off = align256(off + G * (int64_t)path_stride_of(c->max_depth) * 16);
+  L->path = off;       off = align256(off + G * (int64_t)leaves_of(c) * path_stride_of(c->max_depth) * 16);
   L->roots = off;      off = align256(off + G * (int64_t)sizeof(ifx_state));
-  L->leaves = off;     off = align256(off + G * (int64_t)sizeof(ifx_state));
+  L->leaves = off;     off = align256(off + G * (int64_t)leaves_of(c) * (int64_t)sizeof(ifx_state));
   L->sym = off;        off = align256(off + G * (int64_t)sym_cap_of(c->num_sims) * 64);
   L->total = off;
   return IFX_OK;
@@ -292,7 +306,7 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   P.path = (IfxU4*)(b + L.path); P.roots = (ifx_state*)(b + L.roots); P.leaves = (ifx_state*)(b + L.leaves);
   P.sym = (uint8_t*)(b + L.sym); P.sym_cap = sym_cap_of(c->num_sims);
   P.G = c->n_games; P.C = c->nodes_per_game; P.H = c->hash_per_game; P.maxd = c->max_depth;
-  P.path_stride = path_stride_of(c->max_depth);
+  P.path_stride = path_stride_of(c->max_depth); P.leaves_per_wave = leaves_of(c); P.vl_mode = (c->leaves_per_wave > 1 || c->leaves_per_wave == -1) ? 1 : 0;
   P.num_sims = c->num_sims; P.logits = c->policy_is_logits; P.term_budget = c->terminal_sims_per_wave;
   P.dir_alpha = c->dirichlet_alpha; P.dir_eps = c->dirichlet_eps; P.cpuct = c->cpuct; P.seed = c->seed;
   P.debug = nullptr;
@@ -390,6 +404,11 @@ int ifx_mcts_wave_part(ifx_mcts* m, int32_t first_game, int32_t n_games, const f
 #ifdef IFX_HOSTSIM
   static ExpandScratch scratch;
   static RootMirror mirror;
+  static VlScratch vl;
+  if (m->P.vl_mode) {
+    for (int g = first_game; g < g_end; ++g) tree_wave_game_vl(m->P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch, &vl);
+    return ifx_after_launch();
+  }
   for (int g = first_game; g < g_end; ++g) tree_wave_game<false>(m->P, g, nn_pi, pi_stride, nn_v, nn_in, &scratch, &mirror);
   if (m->P.dir_eps > 0.0f) for (int g = first_game; g < g_end; ++g) body_root_noise(m->P, g);
   return ifx_after_launch();
@@ -402,6 +421,11 @@ int ifx_mcts_wave_part(ifx_mcts* m, int32_t first_game, int32_t n_games, const f
       m->ev_made += 1;
     }
     cudaEventRecord(m->ev[m->n_timed][0], (cudaStream_t)stream);
+  }
+  if (m->P.vl_mode) {                        // leaf-parallel performance mode: its own kernel
+    tree_wave_vl_kernel<<<(unsigned)n_games, 32, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in, first_game, g_end);
+    if (timed) { cudaEventRecord(m->ev[m->n_timed][1], (cudaStream_t)stream); m->n_timed += 1; }
+    return ifx_after_launch();
   }
   if (m->P.debug)    // per-warp %globaltimer stamps (tools/trace_wave.py): a separate instantiation, so the product kernel carries none of it
     tree_wave_kernel<true><<<grid, TREE_BLOCK, 0, (cudaStream_t)stream>>>(m->P, nn_pi, pi_stride, nn_v, nn_in, first_game, g_end);

@@ -51,11 +51,15 @@ class BatchedMCTS:
     def __init__(self, n_games: int, num_sims: int, cpuct=1.0, seed: int = 0, nodes_per_game: int | str | None = None,
                  max_depth: int = 352, backend: Backend | None = None, fused_head: bool = False,
                  pad_policy_rows: bool = True, terminal_sims_per_wave: int = 1, dirichlet_alpha: float = 0.0,
-                 dirichlet_eps: float = 0.0, pack_quantum: int | None = None):
+                 dirichlet_eps: float = 0.0, pack_quantum: int | None = None, leaves_per_wave: int = 1):
         """fused_head: the net hands over its last GEMM output (float16 [G,344]: 343 policy logits + the value
         pre-activation, buffer ``nn_head``) and the tree kernel applies softmax / tanh itself.
         terminal_sims_per_wave: how many simulations that end in a terminal state (no net needed) a game may run in
         one wave before it yields (0 = no limit); results do not depend on it, the length of a wave's tail does.
+        leaves_per_wave: 1 = the reference's sequential search (parity mode).  K > 1 = leaf-parallel PERFORMANCE mode with
+        virtual loss (csrc/ifx_tree_vl.cuh): every game hands up to K leaves to each net call (the net buffers have
+        n_games * K rows) and a move needs about num_sims / K calls; visit counts differ from the reference's by
+        construction.  ``search`` then runs until the device reports every game done.
         pack_quantum: granularity of the packed net batch (see ``plan_rows``); None = 256 rows from 2048 games on, 32 rows
         from 64 games on, otherwise no packing; 0 = never pack.
         dirichlet_alpha / dirichlet_eps: optional root noise P <- (1-eps) P + eps Dir(alpha), drawn on the device once
@@ -73,7 +77,10 @@ class BatchedMCTS:
                                     max_depth=max_depth, num_sims=self.num_sims, cpuct=float(np.float32(cpuct)),
                                     seed=int(seed) & (2 ** 64 - 1), policy_is_logits=2 if fused_head else 0,
                                     terminal_sims_per_wave=int(terminal_sims_per_wave),
-                                    dirichlet_alpha=float(dirichlet_alpha), dirichlet_eps=float(dirichlet_eps))
+                                    dirichlet_alpha=float(dirichlet_alpha), dirichlet_eps=float(dirichlet_eps),
+                                    leaves_per_wave=int(leaves_per_wave))
+        self.leaves_per_wave = max(1, int(leaves_per_wave))
+        self._adaptive = int(leaves_per_wave) > 1 or int(leaves_per_wave) == -1
         dll = self.be.dll
         self.layout = _capi.MctsLayout()
         self.be.check(dll.ifx_mcts_get_layout(C.byref(self.cfg), C.byref(self.layout)))
@@ -85,7 +92,7 @@ class BatchedMCTS:
         handle = C.c_void_p()
         self.be.check(dll.ifx_mcts_create(C.byref(self.cfg), self.workspace.data_ptr(), nbytes, C.byref(handle)))
         self._h = handle
-        g = self.n_games
+        g = self.n_games * self.leaves_per_wave                 # rows of the net buffers (K leaves per game in the leaf-parallel mode)
         # net I/O buffers (persistent so the wave + net step can be captured in a CUDA graph)
         self.nn_in = self.be.zeros((g, 4, 7, 7), torch.float32)
         if pad_policy_rows:
@@ -101,9 +108,10 @@ class BatchedMCTS:
         self.evals_run = 0
         self.rows_evaluated = 0                                 # net rows evaluated so far (evals x active rows)
         # leaf gather: the games that search in the current move, and the packed net buffers per batch size
+        g = self.n_games
         if pack_quantum is None:
             pack_quantum = 256 if g >= 2048 else (32 if g >= 64 else 0)
-        self.pack_quantum = int(pack_quantum)
+        self.pack_quantum = int(pack_quantum) if self.leaves_per_wave == 1 else 0     # (packing: sequential mode only)
         self._live_idx = self.be.zeros((g,), torch.int32)
         self._live_n = self.be.zeros((1,), torch.int32)
         self.live_count = g
@@ -242,6 +250,8 @@ class BatchedMCTS:
     def search(self, evaluate, pack: bool = False) -> None:
         """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync, unless
         ``pack``: then ``plan_rows`` first (one sync) so the net only sees the games that search in this move."""
+        if self._adaptive:
+            return self.search_adaptive(evaluate)
         if pack:
             self.plan_rows()
         for _ in range(self.waves_per_search - 1):

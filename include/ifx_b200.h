@@ -145,6 +145,13 @@ typedef struct ifx_mcts_config {
                                once per move, drawn on the device from Philox.  0 (default) = reference behaviour.
                                A root expanded by a wave yields until the next wave (its priors are perturbed in
                                between), so a move then needs num_sims+2 calls of ifx_mcts_wave                     */
+  int32_t leaves_per_wave;  /* 0 or 1: the reference's sequential search (one leaf per game and wave; the parity mode).
+                               K = 2..16: leaf-parallel PERFORMANCE mode with virtual loss (csrc/ifx_tree_vl.cuh): a game
+                               collects up to K leaves per wave, row g*K + j of nn_pi / nn_v / nn_in belongs to leaf j of
+                               game g (the buffers have n_games*K rows), a move needs about num_sims/K net calls; keep
+                               calling ifx_mcts_wave until ifx_mcts_status shows sims_done == num_sims for every game.
+                               Visit counts differ from the sequential search by construction.  (-1: the leaf-parallel
+                               kernel with K = 1, which must reproduce the sequential search bit for bit -- a test hook) */
 } ifx_mcts_config;
 
 typedef struct ifx_mcts ifx_mcts;
