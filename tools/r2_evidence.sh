@@ -23,6 +23,3 @@ python tools/trace_wave.py 4096 default 2>&1 | tail -12 > gpurun_out/${T}_trace_
 python tools/trace_wave.py 4096 stub 2>&1 | tail -16 > gpurun_out/${T}_trace_stub.log
 for f in default stub reference sims200; do python tools/fmt_bench.py < gpurun_out/${T}_bench_$f.json 2>/dev/null || cut -c1-600 gpurun_out/${T}_bench_$f.json; tail -2 gpurun_out/${T}_bench_$f.err; done
 cut -c1-700 gpurun_out/${T}_bench_rules.json
-# stall samples per source line over 40 launches each (tools/stall_profile.py reads these)
-ncu --section SourceCounters --section WarpStateStats --clock-control none --import-source on -k regex:tree_wave -s 350 -c 40 -o gpurun_out/stall_default_${T} -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extra-rooflines > gpurun_out/ncu6.log 2>&1
-ncu --section SourceCounters --section WarpStateStats --clock-control none --import-source on -k regex:tree_wave -s 350 -c 40 -o gpurun_out/stall_stub_${T} -f python bench.py --net stub --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu7.log 2>&1
