@@ -47,7 +47,7 @@ def parse_args():
                     help="selfplay = the headline (BASELINE configs[2]); rules = the rules kernel alone (configs[1] shape)")
     ap.add_argument("--states", type=int, default=4 * 1024 * 1024, help="states per launch for --workload rules")
     ap.add_argument("--nodes", type=int, default=None, help="node pool slots per game (default: mcts_batched.default_pool_size)")
-    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
                     help="2 = search the games as two halves on two streams inside the captured move (tree wave of one half "

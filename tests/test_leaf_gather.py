@@ -161,3 +161,28 @@ def test_two_stream_capture_equals_single_stream(cuda_backend, net):
     else:                                                      # (batch-size dependent kernel choices may move a prior by an ulp)
         same = (outs[0][0] == outs[1][0]).all(dim=2).float().mean()
         assert float(same) > 0.97
+
+
+@pytest.mark.gpu
+def test_packed_cuda_graphs_per_bucket_equal_the_dense_eager_search(cuda_backend):
+    """2 304 games whose episodes end at different moves: the captured move is re-used per net batch size (one graph per
+    bucket of 256 rows, the live count read on the device), and every bucket must give what the dense, un-captured search
+    gives -- visit counts and actions of every game and move."""
+    from inflexion_b200.stubnet import stub_kernel_evaluator
+    be = cuda_backend
+    G, sims, moves = 2304, 12, 9
+    max_turns = 2 + (np.arange(G) % 7)                         # episodes of 3..9 moves: the live set shrinks move by move
+    outs, buckets = [], []
+    for graph in (False, True):
+        eng = SelfPlayEngine(G, sims, None, temp_threshold=3, seed=8, max_turns=343, backend=be, use_graph=graph)
+        eng.evaluate = stub_kernel_evaluator(eng.mcts)
+        eng.mcts.pack_quantum = 256 if graph else 0
+        eng.mcts.reset(start_states(G, max_turns))
+        for _ in range(moves):
+            eng.play_move()
+            buckets.append(eng.mcts.rows_active)
+        eng.mcts.raise_on_faults()
+        torch.cuda.synchronize()
+        outs.append((eng.ex_counts[:moves].clone(), eng.ex_actions[:moves].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert len(set(buckets[moves:])) >= 4 and min(buckets[moves:]) <= 512      # several bucket sizes were captured and replayed
