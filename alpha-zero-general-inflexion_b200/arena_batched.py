@@ -20,7 +20,8 @@ from .state import STATE_DTYPE, pack_states
 
 class BatchedArena:
     def __init__(self, evaluate, num_sims: int, cpuct=1.0, opponent: str = "random", seed: int = 0,
-                 max_turns: int = 343, backend: Backend | None = None, fused_head: bool = False, record: bool = False):
+                 max_turns: int = 343, backend: Backend | None = None, fused_head: bool = False, record: bool = False,
+                 leaves_per_wave: int = 1):
         if opponent not in ("random", "greedy"):
             raise ValueError("opponent must be 'random' or 'greedy'")
         self.be = backend or default_backend()
@@ -29,6 +30,9 @@ class BatchedArena:
         # record: keep every game's move sequence and result of the last playGames call (this rank's games):
         # ``last_actions`` int32 [plies, games] (-1 once a game is over), ``last_results`` (+1 RED won, -1 BLUE, 0 draw)
         self.record, self.last_actions, self.last_results = bool(record), None, None
+        # leaves_per_wave > 1: the MCTS player searches leaf-parallel with virtual loss (performance mode: K times larger
+        # net batches for the few games of an Arena; its moves then differ from the reference's sequential search)
+        self.leaves_per_wave = int(leaves_per_wave)
 
     def _opponent_actions(self, states, ply):
         if self.opponent == "random":
@@ -63,7 +67,8 @@ class BatchedArena:
         starts = pack_states(np.zeros((num, 49), dtype=np.int64), np.where(red_first, 1, -1), 0, 0, self.max_turns,
                              tags=np.arange(lo, hi))
         states = self.be.states_tensor(starts)
-        mcts = BatchedMCTS(num, self.num_sims, self.cpuct, seed=self.seed, backend=self.be, fused_head=self.fused_head)
+        mcts = BatchedMCTS(num, self.num_sims, self.cpuct, seed=self.seed, backend=self.be, fused_head=self.fused_head,
+                           leaves_per_wave=self.leaves_per_wave)
         started = False
         played = []
         for ply in range(self.max_turns + 2):

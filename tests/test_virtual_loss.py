@@ -116,3 +116,15 @@ def test_object_api_leaves_per_wave(backend, monkeypatch):
     game = InflexionGame(7, max_turns=343, max_power=6)
     probs = MCTS(Net(), dotdict({"numMCTSSims": 30, "cpuct": 1, "leavesPerWave": 6}), seed=5, backend=backend).getActionProb(game, temp=1)
     assert abs(probs.sum() - 1.0) < 1e-12 and (probs[:294] == 0).all()      # empty board: only spawns are valid
+
+
+def test_batched_arena_leaf_parallel(backend):
+    """BatchedArena(leaves_per_wave=K): complete games, valid results, K times larger net batches."""
+    from inflexion_b200.arena_batched import BatchedArena
+    rows = []
+
+    def evaluate(x):
+        rows.append(x.shape[0])
+        return stub_policy_value(x)
+    res = BatchedArena(evaluate, 12, opponent="greedy", seed=4, max_turns=10, backend=backend, leaves_per_wave=4).playGames(6, shard=False)
+    assert sum(res) == 6 and set(rows) == {24}
