@@ -105,7 +105,8 @@ class Coach:
         eng = SelfPlayEngine(per, int(self.args.numMCTSSims), evaluate, cpuct=self.args.cpuct,
                              temp_threshold=int(self.args.tempThreshold), seed=seed, max_turns=self.game._max_turns,
                              game_id_base=game_id_base + rank * per, fused_head=fused,
-                             nodes_per_game=dict(self.args).get("nodesPerGame", "auto"))
+                             nodes_per_game=dict(self.args).get("nodesPerGame", "auto"),
+                             leaves_per_wave=int(dict(self.args).get("leavesPerWave", 1)))
         # the ranks stop together, as soon as every game everywhere is over (all-gather shapes agree; no rank keeps
         # searching finished games)
         eng.play_episode(collective=world > 1)

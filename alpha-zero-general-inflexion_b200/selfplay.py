@@ -28,7 +28,7 @@ class SelfPlayEngine:
                  record: bool = True, use_graph: bool | None = None, backend: Backend | None = None,
                  fused_head: bool = False, auto_restart: bool = False, restart_stride: int | None = None,
                  record_moves: int | None = None, dirichlet_alpha: float = 0.0, dirichlet_eps: float = 0.0,
-                 streams: int = 1):
+                 streams: int = 1, leaves_per_wave: int = 1):
         """evaluate(nn_in f32 [G,4,7,7]) -> (pi f32 [G,343], v f32 [G]) on the device (e.g. nnet.predict_batch); with
         ``fused_head`` it is evaluate(nn_in, out f16 [G,344]) writing the raw head output (e.g. nnet.predict_head) and
         the tree kernel does the softmax / tanh.  ``auto_restart``: a game that ends starts its next episode at once
@@ -36,13 +36,17 @@ class SelfPlayEngine:
         global game count when several ranks play).  ``streams`` = 2: inside the captured move the games are searched as
         two halves on two streams, so the tree wave of one half runs while the net evaluates the other half (the
         latency-bound wave fills issue slots the tensor-bound convolutions leave idle); results are identical -- games
-        are independent.  Used with CUDA graphs and a dense batch only."""
+        are independent.  Used with CUDA graphs and a dense batch only.  ``leaves_per_wave`` = K > 1: the leaf-parallel
+        performance mode (virtual loss; BatchedMCTS) -- for small sets of games, where the sequential search leaves the
+        net with tiny batches; eager waves, not the reference's visit counts."""
         self.be = backend or default_backend()
         self.G, self.num_sims, self.temp_threshold = int(n_games), int(num_sims), int(temp_threshold)
         self.max_turns, self.game_id_base = int(max_turns), int(game_id_base)
         self.evaluate = evaluate
         self.mcts = BatchedMCTS(self.G, num_sims, cpuct, seed=seed, nodes_per_game=nodes_per_game, backend=self.be,
-                                fused_head=fused_head, dirichlet_alpha=dirichlet_alpha, dirichlet_eps=dirichlet_eps)
+                                fused_head=fused_head, dirichlet_alpha=dirichlet_alpha, dirichlet_eps=dirichlet_eps,
+                                leaves_per_wave=leaves_per_wave)
+        self.leaf_parallel = int(leaves_per_wave) > 1
         self.record = record
         # a game lasts at most max_turns+1 moves; continuous play (auto_restart) records up to ``record_moves`` moves
         self.max_moves = int(record_moves or self.max_turns + 1)
@@ -54,11 +58,11 @@ class SelfPlayEngine:
             self.ex_after = self.be.empty((self.max_moves, self.G, 64), torch.uint8)   # root after the move (its outcome)
             self.ex_counts = self.be.empty((self.max_moves, self.G, 343), torch.int32)
             self.ex_actions = self.be.empty((self.max_moves, self.G), torch.int32)
-        self.use_graph = self.be.is_cuda if use_graph is None else bool(use_graph)
+        self.use_graph = (self.be.is_cuda if use_graph is None else bool(use_graph)) and not self.leaf_parallel
         self._graphs = {}                                         # net batch size -> captured search of one move
         # fixed sets of episodes (no auto_restart) thin out as games end: the net then runs on the live games only
         # (BatchedMCTS.plan_rows: one host read per move, a captured graph per batch size)
-        self.pack = not self.auto_restart
+        self.pack = not self.auto_restart and not self.leaf_parallel
         self.streams = 2 if (int(streams) == 2 and self.G >= 2) else 1
         self._side = None
         self.move = 0
@@ -125,6 +129,10 @@ class SelfPlayEngine:
         """The numMCTSSims loop for all games.  ``wave_timer`` (optional): True launches every tree wave outside the
         CUDA graph (so the library can bracket it with events, see BatchedMCTS.wave_timing); a callable wraps each
         launch instead."""
+        if self.leaf_parallel:                                   # waves until the device reports every game done
+            self.mcts.search(self.evaluate)
+            self.my_launches += self.mcts.waves_per_search
+            return
         if wave_timer is True:
             wave_timer = lambda fn: fn()  # noqa: E731
         if self.pack and self.mcts.plan_rows() and self.mcts.live_count == 0:

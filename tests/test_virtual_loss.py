@@ -128,3 +128,15 @@ def test_batched_arena_leaf_parallel(backend):
         return stub_policy_value(x)
     res = BatchedArena(evaluate, 12, opponent="greedy", seed=4, max_turns=10, backend=backend, leaves_per_wave=4).playGames(6, shard=False)
     assert sum(res) == 6 and set(rows) == {24}
+
+
+def test_selfplay_engine_leaf_parallel_emits_examples(backend):
+    """SelfPlayEngine(leaves_per_wave=K): whole episodes, examples with the reference's shapes and value targets."""
+    from inflexion_b200.selfplay import SelfPlayEngine
+    eng = SelfPlayEngine(3, 16, lambda x: stub_policy_value(x), temp_threshold=3, seed=2, max_turns=6, backend=backend,
+                         leaves_per_wave=4)
+    moves = eng.play_episode()
+    eng.mcts.raise_on_faults()
+    planes, pi, v = eng.examples()
+    assert moves == 7 and planes.shape == (3 * 7 * 36, 4, 7, 7) and np.allclose(pi.sum(axis=1), 1.0)
+    assert set(np.round(np.abs(v), 4).tolist()) <= {1.0, 0.0001}
