@@ -48,7 +48,8 @@ class NNetWrapper(NeuralNet):
         ranks' draws."""
         dist = torch.distributed if torch.distributed.is_available() and torch.distributed.is_initialized() else None
         world = dist.get_world_size() if dist else 1
-        optimizer = optim.Adam(self.nnet.parameters())
+        # (the reference's optimizer, NNet.py:40; on a GPU the fused implementation: one kernel per step instead of a dozen)
+        optimizer = optim.Adam(self.nnet.parameters(), fused=True) if self.device.type == "cuda" else optim.Adam(self.nnet.parameters())
         # ``examples`` is the reference's list of (planes, pi, v), or an on-demand set (selfplay.ExampleSet /
         # ExampleUnion: ``len`` + ``batch(ids)``) that expands only the rows a batch draws
         on_demand = hasattr(examples, "batch")
@@ -103,23 +104,37 @@ class NNetWrapper(NeuralNet):
                 print("EPOCH ::: " + str(epoch + 1))
             self.nnet.train()
             pi_losses, v_losses = AverageMeter(), AverageMeter()
-            for _ in range(steps):
-                ids = np.random.randint(len(examples), size=per_rank_batch)
+            # Batches are prepared a chunk of steps at a time (one index draw, one expansion / one host-to-device copy
+            # for the whole chunk, sliced per step) and the loss meters are read once per epoch: no per-step launch
+            # storm and no per-step host sync.  The draws are the same uniform-with-replacement samples (NNet.py:52).
+            chunk = 16
+            loss_sum = torch.zeros(2, dtype=torch.float64, device=self.device)
+            done = 0
+            while done < steps:
+                k = min(chunk, steps - done)
+                ids = np.random.randint(len(examples), size=k * per_rank_batch)
                 if on_demand:
-                    boards, target_pis, target_vs = (t.to(self.device) for t in examples.batch(ids))
+                    boards_c, pis_c, vs_c = (t.to(self.device) for t in examples.batch(ids))
                 else:
-                    ids = torch.from_numpy(ids)
-                    boards = boards_all[ids].to(self.device, non_blocking=True)
-                    target_pis = pis_all[ids].to(self.device, non_blocking=True)
-                    target_vs = vs_all[ids].to(self.device, non_blocking=True)
-                out_pi, out_v = model(boards)
-                l_pi = self.loss_pi(target_pis, out_pi)
-                l_v = self.loss_v(target_vs, out_v)
-                optimizer.zero_grad(set_to_none=False)
-                (l_pi + l_v).backward()                      # (DDP: the gradient buckets are all-reduced while this runs)
-                optimizer.step()
-                pi_losses.update(l_pi.item(), boards.size(0))
-                v_losses.update(l_v.item(), boards.size(0))
+                    ids_t = torch.from_numpy(ids)
+                    boards_c = boards_all[ids_t].to(self.device, non_blocking=True)
+                    pis_c = pis_all[ids_t].to(self.device, non_blocking=True)
+                    vs_c = vs_all[ids_t].to(self.device, non_blocking=True)
+                for j in range(k):
+                    sl = slice(j * per_rank_batch, (j + 1) * per_rank_batch)
+                    boards, target_pis, target_vs = boards_c[sl], pis_c[sl], vs_c[sl]
+                    out_pi, out_v = model(boards)
+                    l_pi = self.loss_pi(target_pis, out_pi)
+                    l_v = self.loss_v(target_vs, out_v)
+                    optimizer.zero_grad(set_to_none=False)
+                    (l_pi + l_v).backward()                  # (DDP: the gradient buckets are all-reduced while this runs)
+                    optimizer.step()
+                    loss_sum += torch.stack([l_pi.detach(), l_v.detach()]).to(torch.float64)
+                done += k
+            if steps:
+                lp, lv = (loss_sum / steps).tolist()
+                pi_losses.update(lp, steps * per_rank_batch)
+                v_losses.update(lv, steps * per_rank_batch)
             history.append((pi_losses.avg, v_losses.avg))
             if verbose:
                 print(f"  Loss_pi={pi_losses} Loss_v={v_losses}")
