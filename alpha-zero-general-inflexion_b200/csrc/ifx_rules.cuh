@@ -36,8 +36,10 @@ IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) {     // m = move type
   const uint64_t src = 1ull << cell;
   uint64_t own = ifx_own(s), opp = ifx_opp(s);
   uint64_t p0 = s.p0, p1 = s.p1, p2 = s.p2;
+  int total = (int)s.total_power;                           // kept incrementally (three 64-bit popcounts otherwise)
   if (m == IFX_SPAWN) {                                      // :278-280  board[r,q] = player
     own |= src; p0 |= src;
+    total += 1;
   } else {                                                   // :281-289
     const int k = ifx_cell_power(s, cell);
     const int dr = ifx_dir_dr(m), dq = ifx_dir_dq(m);
@@ -54,6 +56,8 @@ IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) {     // m = move type
     const uint64_t c1 = p1 & c0;    p1 ^= c0;
     p2 ^= c1;
     const uint64_t over = p0 & p1 & p2;                      // reached 7: stack is destroyed
+    total -= 7 * ifx_popc64(over);                           // a spread moves the stack's k units onto k cells: the sum only
+                                                             // changes where a cell reaches 7 and vanishes
     const uint64_t gone = over | src;                        // :289 source cell emptied
     p0 &= ~gone; p1 &= ~gone; p2 &= ~gone;
     own = (own | line) & ~gone;
@@ -61,7 +65,7 @@ IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) {     // m = move type
   }
   s.p0 = p0; s.p1 = p1; s.p2 = p2;
   if (s.player) { s.blue = own; s.red = opp; } else { s.red = own; s.blue = opp; }
-  s.total_power = (uint8_t)ifx_total_power(s);
+  s.total_power = (uint8_t)total;
   // outcome for the mover, first match wins (:294-306)
   int out = IFX_ONGOING;
   if (m != IFX_SPAWN && opp == 0) {

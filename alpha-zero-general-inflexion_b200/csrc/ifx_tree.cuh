@@ -437,14 +437,16 @@ IFX_D void tree_rows_from_mirror(const RootMirror* M, RowRegs& R) {
   R.key = M->key;
 }
 
-// `rows` = where groups beyond the first come from (the node's rows in HBM, or the root mirror).
+// Groups beyond the first (a node with more than 128 valid actions: rare) come from `mirror_rows` (the root mirror) or,
+// when that is null, from the node's rows in HBM -- whose address is only worked out if such a group exists.
 // Returns the compact index of the chosen edge (or -1), its raw N word (it carries the child hint) and its Q.
-IFX_D int tree_select(const TreeParams& P, RowRegs& R, const float* rows, int nv, uint32_t* chosen_raw, float* chosen_q) {
+IFX_D int tree_select(const TreeParams& P, RowRegs& R, const float* mirror_rows, int g, int slot, int nv, uint32_t* chosen_raw,
+                      float* chosen_q) {
   const float sq_seen = R.head.sq_seen, sq_unseen = R.head.sq_unseen;
   LaneVar<float> bu, bq; LaneVar<int> ba; LaneVar<uint32_t> braw;
   IFX_FOR_LANES(l) { bu[l] = -INFINITY; bq[l] = 0.0f; ba[l] = 0x7fffffff; braw[l] = 0u; }
   for (int j = 0; IFX_GROUP * j < nv; ++j) {
-    if (j > 0) tree_rows_load_group(rows, j, R);
+    if (j > 0) tree_rows_load_group(mirror_rows ? mirror_rows : tree_row(P, g, slot, 0), j, R);
     IFX_FOR_LANES(l) {
       float best = bu[l], qsel = bq[l]; int arg = ba[l]; uint32_t raw = braw[l];
       // ascending order inside the lane and across groups, strict '>' keeps the lowest index on ties
@@ -963,7 +965,7 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
       uint32_t raw = 0; float qsel = 0.0f;
       const ValidSet V = ifx_valid_set(ifx_own(st), ifx_spawn_mask(st));
       const bool at_root = depth == 0 && slot == mirror_slot;
-      const int ci = tree_select(P, rows, at_root ? mirror->rows : tree_row(P, g, slot, 0), V.nv, &raw, &qsel);
+      const int ci = tree_select(P, rows, at_root ? mirror->rows : nullptr, g, slot, V.nv, &raw, &qsel);
       if (ci < 0) { G.faults |= IFX_F_NOVALID; break; }
       if (depth >= P.maxd) { G.faults |= IFX_F_DEPTH; break; }
       // request the hinted child's rows FIRST -- the hint came out of the arg-max with the edge -- so that the loads
