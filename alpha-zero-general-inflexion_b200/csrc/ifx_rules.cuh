@@ -32,7 +32,28 @@ IFX_HD int ifx_num_valid(const ifx_state& s) { return 6 * ifx_popc64(ifx_own(s))
 
 // execute_move, InflexionGame.py:273-310 (the action must be valid).  Updates s in place:
 // board, outcome (relative to the NEW side to move), turn+1, player flipped.
-IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) {     // m = move type 0..6, cell = r*7+q
+// the k cells a stack of power k at `cell` lands on when spread in direction m (k <= 6 < 7: all distinct, none the source)
+IFX_HD uint64_t ifx_spread_line(int m, int cell, int k) {
+  const int dr = ifx_dir_dr(m), dq = ifx_dir_dq(m);
+  int r = cell / IFX_N, q = cell - r * IFX_N;
+  uint64_t line = 0;
+  for (int i = 0; i < k; ++i) {
+    r += dr; q += dq;
+    r = r < 0 ? r + IFX_N : (r >= IFX_N ? r - IFX_N : r);
+    q = q < 0 ? q + IFX_N : (q >= IFX_N ? q - IFX_N : q);
+    line |= 1ull << (r * IFX_N + q);
+  }
+  return line;
+}
+#if !defined(IFX_HOSTSIM) && defined(IFX_WITH_LINE_LUT)
+// The same masks as a table in constant memory, [6 directions][49 cells][6 powers] (14 KB, filled by ifx_mcts_create):
+// ONE uniform-indexed constant load where every lane of a warp steps the same board (the tree kernels); the rules
+// kernels, one state per thread, keep the loop (divergent constant addresses would serialise).
+__constant__ uint64_t g_ifx_line_lut[6 * IFX_CELLS * 6];
+#endif
+
+template <bool LUT>
+IFX_HD void ifx_apply_move_t(ifx_state& s, int m, int cell) {   // m = move type 0..6, cell = r*7+q
   const uint64_t src = 1ull << cell;
   uint64_t own = ifx_own(s), opp = ifx_opp(s);
   uint64_t p0 = s.p0, p1 = s.p1, p2 = s.p2;
@@ -42,15 +63,12 @@ IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) {     // m = move type
     total += 1;
   } else {                                                   // :281-289
     const int k = ifx_cell_power(s, cell);
-    const int dr = ifx_dir_dr(m), dq = ifx_dir_dq(m);
-    int r = cell / IFX_N, q = cell - r * IFX_N;
-    uint64_t line = 0;                                       // the k cells the stack lands on (k <= 6 < 7: distinct)
-    for (int i = 0; i < k; ++i) {
-      r += dr; q += dq;
-      r = r < 0 ? r + IFX_N : (r >= IFX_N ? r - IFX_N : r);
-      q = q < 0 ? q + IFX_N : (q >= IFX_N ? q - IFX_N : q);
-      line |= 1ull << (r * IFX_N + q);
-    }
+    uint64_t line;                                           // the k cells the stack lands on
+#if !defined(IFX_HOSTSIM) && defined(IFX_WITH_LINE_LUT)
+    if (LUT) line = k > 0 ? g_ifx_line_lut[(m * IFX_CELLS + cell) * 6 + (k - 1)] : 0ull;
+    else
+#endif
+      line = ifx_spread_line(m, cell, k);
     // |x| + 1 on the three bit planes, 7 -> removed (:287-288)
     const uint64_t c0 = p0 & line;  p0 ^= line;
     const uint64_t c1 = p1 & c0;    p1 ^= c0;
@@ -83,9 +101,10 @@ IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) {     // m = move type
   s.outcome = (uint8_t)(out == IFX_WON ? IFX_LOST : (out == IFX_LOST ? IFX_WON : out));
 }
 
+IFX_HD void ifx_apply_move(ifx_state& s, int m, int cell) { ifx_apply_move_t<false>(s, m, cell); }
 IFX_HD void ifx_apply(ifx_state& s, int action) {
   const int m = action / IFX_CELLS;
-  ifx_apply_move(s, m, action - m * IFX_CELLS);
+  ifx_apply_move_t<false>(s, m, action - m * IFX_CELLS);
 }
 
 // Value of a terminal state as MCTS.py:87 reads it (GameOutcome.value, flags.py:32-36).

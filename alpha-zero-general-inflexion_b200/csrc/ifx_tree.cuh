@@ -13,6 +13,7 @@
 // record instead (root slot, next free slot, hash position of the pending leaf, the path itself, which
 // lives one level per lane in registers and is spilled to HBM only while a leaf waits for the net).
 #pragma once
+#define IFX_WITH_LINE_LUT 1          // (this translation unit owns the constant-memory table of spread lines)
 #include "ifx_rules.cuh"
 #include "ifx_philox.cuh"
 
@@ -642,9 +643,10 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
     IFX_FOR_LANES(l) {
       float x[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int ci = l + 32 * t;
-        x[t] = ci < V.nv ? ifx_h2f(sh[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)]) : -INFINITY;
+      for (int t = 0; t < 4; ++t) {                       // (32 t < nv is lane-uniform: with 86 valid actions on average the
+        const int ci = l + 32 * t;                          //  fourth pass, often the third, is skipped by the whole warp)
+        x[t] = -INFINITY;
+        if (32 * t < V.nv && ci < V.nv) x[t] = ifx_h2f(sh[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)]);
       }
       float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
       for (int ci = l + 128; ci < V.nv; ci += 32) {
@@ -692,12 +694,15 @@ IFX_D int tree_expand(const TreeParams& P, int g, IfxGame& G, const ifx_state& l
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int ci = l + 32 * t;
-        v[t] = (ci < V.nv && !uniform) ? buf[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)] : 1.0f;
+        v[t] = 1.0f;
+        if (32 * t < V.nv && ci < V.nv && !uniform) v[t] = buf[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)];
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {                         // (a dummy 1.0 keeps idle lanes out of the division's slow path)
-        const float q = ifx_fdiv(v[t], total);
-        if (l + 32 * t < V.nv) prow[l + 32 * t] = q;
+        if (32 * t < V.nv) {                                // lane-uniform: no division for a pass nobody needs
+          const float q = ifx_fdiv(v[t], total);
+          if (l + 32 * t < V.nv) prow[l + 32 * t] = q;
+        }
       }
       for (int ci = l + 128; ci < V.nv; ci += 32)
         prow[ci] = ifx_fdiv(uniform ? 1.0f : buf[tree_entry_action(S, ci, V.n_own, spread, inv_n_own)], total);
@@ -990,7 +995,7 @@ IFX_D void tree_wave_game(const TreeParams& P0, int g0, const float* nn_pi, int6
       }
       if (DBG && depth == 1 && dbg_t4 == 0) dbg_t4 = ifx_now_ns();
       if (DBG) dbg_depth = depth > dbg_depth ? depth : dbg_depth;
-      ifx_apply_move(st, mv_type, mv_cell);                 // MCTS.py:132
+      ifx_apply_move_t<true>(st, mv_type, mv_cell);         // MCTS.py:132 (spread line from the constant-memory table)
     }
     if (G.pending) break;
   }

@@ -315,6 +315,21 @@ int ifx_mcts_create(const ifx_mcts_config* c, void* ws, size_t bytes, ifx_mcts**
   // register-limited number of CTAs per SM (IFX_WAVE_MIN_BLOCKS) is also what shared memory allows
   cudaFuncSetAttribute(tree_wave_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(tree_wave_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  {                                                         // spread-line table -> constant memory (idempotent)
+    static const int DR[6] = {1, -1, 0, 0, 1, -1}, DQ[6] = {0, 0, 1, -1, -1, 1};   // (dr, dq) of move 0..5, InflexionGame.py:15-21
+    static uint64_t lut[6 * IFX_CELLS * 6];
+    for (int mv = 0; mv < 6; ++mv)
+      for (int cell = 0; cell < IFX_CELLS; ++cell) {
+        int r = cell / IFX_N, q = cell % IFX_N;
+        uint64_t line = 0;
+        for (int k = 1; k <= 6; ++k) {
+          r = (r + DR[mv] + IFX_N) % IFX_N; q = (q + DQ[mv] + IFX_N) % IFX_N;
+          line |= 1ull << (r * IFX_N + q);
+          lut[(mv * IFX_CELLS + cell) * 6 + (k - 1)] = line;
+        }
+      }
+    if (cudaMemcpyToSymbol(g_ifx_line_lut, lut, sizeof(lut)) != cudaSuccess) { delete m; return ifx_set_cuda_error((int)cudaGetLastError()); }
+  }
   tree_sym_lut_kernel<<<126, 64>>>();                       // idempotent; ordered before any later launch of this process
   if (cudaDeviceSynchronize() != cudaSuccess) { delete m; return ifx_set_cuda_error((int)cudaGetLastError()); }
 #endif

@@ -225,7 +225,7 @@ IFX_D void tree_wave_game_vl(const TreeParams& P0, int g0, const float* nn_pi, i
       int mv_type, mv_cell;
       tree_compact_to_move(V, ci, &mv_type, &mv_cell);
       depth += 1;
-      ifx_apply_move(st, mv_type, mv_cell);
+      ifx_apply_move_t<true>(st, mv_type, mv_cell);
     }
     if (stop) break;
   }
