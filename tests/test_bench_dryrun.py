@@ -115,3 +115,22 @@ def test_reference_arm_prints_one_line_and_other_ranks_stay_silent(monkeypatch, 
     line = json.loads(capsys.readouterr().out.strip())
     assert line["impl"] == "reference" and line["value"] == 10.0 and line["e2e"]["value"] == 10.0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["ms_per_step"] == 500.0
+
+
+def test_reference_copy_is_hash_checked(tmp_path):
+    """oracle/make_ref.py: the staged reference is verified against the SHA-256 manifest written at staging time; an
+    edited copy is refused (bench.py then falls back to the labelled port instead of timing a modified reference)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import make_ref
+    finally:
+        sys.path.pop(0)
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs /root/reference (build container)")
+    dest = str(tmp_path / "_ref")
+    make_ref.stage("/root/reference", dest)
+    assert make_ref.verify(dest)
+    with open(os.path.join(dest, "MCTS.py"), "a") as f:
+        f.write("\n# edited\n")
+    assert not make_ref.verify(dest)
+    assert not make_ref.verify(str(tmp_path / "missing"))
