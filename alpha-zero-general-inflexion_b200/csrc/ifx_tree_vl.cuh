@@ -155,7 +155,9 @@ IFX_D void tree_wave_game_vl(const TreeParams& P0, int g0, const float* nn_pi, i
   G.pending = 0;
   // ---- phase B: collect up to K new leaves; later descents see the earlier ones' edges with a virtual loss ----
   int n_leaf = 0;
-  int term_left = P.term_budget > 0 ? P.term_budget : 0x7fffffff;
+  // terminal simulations need no net: a wave may run K times the sequential mode's budget of them, so that a game whose
+  // search keeps ending in terminal states (a forced win at the root) still completes about K simulations per wave
+  int term_left = P.term_budget > 0 ? P.term_budget * K : 0x7fffffff;
   const ifx_state root = P.roots[g];
   while (!G.faults && n_leaf < K && G.sims_done + n_leaf < P.num_sims && term_left > 0) {
     ifx_state st = root;

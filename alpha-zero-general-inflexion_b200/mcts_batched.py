@@ -260,16 +260,27 @@ class BatchedMCTS:
         self.wave()
 
     def search_adaptive(self, evaluate) -> None:
-        """Same result as ``search`` but asks the device after every wave whether any game still waits for the
-        net (one small read-back per wave) and stops as soon as none does: the net is called exactly as often
-        as the reference calls ``predict``.  Used by the object-per-game drop-in, where a call is expensive."""
+        """Same result as ``search`` but asks the device whether any game still waits for the net (one small read-back)
+        and stops as soon as none does.  Sequential mode (the object-per-game drop-in, where a ``predict`` call is
+        expensive): a read-back after every wave, so the net is called exactly as often as the reference calls
+        ``predict``.  Leaf-parallel mode: a wave completes at most ``leaves_per_wave`` net-evaluated simulations per
+        game, so after a look the next ceil(remaining / K) - 1 waves cannot be the last ones and run without a
+        read-back."""
+        self.wave()
+        st = self.status()
         while True:
-            self.wave()
-            st = self.status()
-            if bool(((st[:, 0] >= self.num_sims) | (st[:, 2] != 0)).all()):
+            done = (st[:, 0] >= self.num_sims) | (st[:, 2] != 0)
+            if bool(done.all()):
                 return
             if bool(st[:, 1].any()):                         # (a game that yielded on its terminal budget needs no net)
                 self.feed(evaluate)
+            if self.leaves_per_wave > 1:
+                remaining = int((self.num_sims - st[:, 0])[~done].max())
+                for _ in range(max(0, -(-remaining // self.leaves_per_wave) - 1)):
+                    self.wave()
+                    self.feed(evaluate)
+            self.wave()
+            st = self.status()
 
     def wave_timing(self, enable: bool) -> None:
         """Bracket every (un-captured) wave launch with CUDA events inside the library call (see ifx_mcts_wave_timing)."""
