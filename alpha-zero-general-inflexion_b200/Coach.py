@@ -160,7 +160,7 @@ class Coach:
                 for name in ("random", "greedy"):
                     arena = BatchedArena(evaluate, int(self.args.numMCTSSims), self.args.cpuct, opponent=name,
                                          seed=self._job_seed(), max_turns=self.game._max_turns, fused_head=fused,
-                                         leaves_per_wave=int(opts.get("leavesPerWave", 1)))
+                                         leaves_per_wave=int(opts.get("leavesPerWave", 1)), capture=True)
                     p1wins, p2wins, draws = arena.playGames(int(self.args.arenaCompare))
                     log.info(f"NEW/{name.capitalize()}Player WINS : {p1wins} / {p2wins} ; DRAWS : {draws}")
                 continue

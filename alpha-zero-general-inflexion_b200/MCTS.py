@@ -56,6 +56,19 @@ class MCTS:
             vs.append(np.asarray(v, dtype=np.float32).reshape(-1)[0])
         return (torch.as_tensor(np.stack(pis)).to(nn_in.device), torch.as_tensor(np.asarray(vs, dtype=np.float32)).to(nn_in.device))
 
+    def _run_search(self) -> None:
+        """The numMCTSSims loop.  With a device net (``predict_batch`` on the tree's GPU, and a ``weights_version`` to
+        tell when it changes) every (net, wave) step is replayed from a CUDA graph -- identical results, one launch per
+        simulation instead of a dozen; ``args.captureSearch = False`` keeps the eager loop.  Host nets (the
+        reference-style ``predict``) are called leaf by leaf, exactly as often as the reference calls them."""
+        t, n = self._tree, self.nnet
+        if (t.be.is_cuda and dict(self.args).get("captureSearch", True) and hasattr(n, "predict_batch")
+                and hasattr(n, "weights_version") and getattr(n, "device", None) == t.be.device):
+            t.search_captured(n.predict_batch, version=(id(n), n.weights_version))
+        else:
+            t.search_adaptive(self._evaluate)
+        t.raise_on_faults()
+
     def _install_root(self, game) -> None:
         sims, cpuct = int(self.args.numMCTSSims), self.args.cpuct
         state = game._state.copy()
@@ -84,8 +97,7 @@ class MCTS:
         if not (isinstance(temp, (int, float)) and temp >= 0):
             raise ValueError("temp must be a non-negative number")
         self._install_root(game)
-        self._tree.search_adaptive(self._evaluate)
-        self._tree.raise_on_faults()
+        self._run_search()
         counts = self._tree.root_stats()["counts"][0].cpu().numpy().astype(np.int64)
         if temp == 0:
             best = int(self._tree.sample_actions(0)[0])                   # uniform among the arg-max ties, on device
@@ -102,8 +114,7 @@ class MCTS:
         try:
             self.args["numMCTSSims"] = 1
             self._install_root(game)
-            self._tree.search_adaptive(self._evaluate)
-            self._tree.raise_on_faults()
+            self._run_search()
         finally:
             self.args["numMCTSSims"] = saved
 

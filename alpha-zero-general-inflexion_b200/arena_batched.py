@@ -21,7 +21,7 @@ from .state import STATE_DTYPE, pack_states
 class BatchedArena:
     def __init__(self, evaluate, num_sims: int, cpuct=1.0, opponent: str = "random", seed: int = 0,
                  max_turns: int = 343, backend: Backend | None = None, fused_head: bool = False, record: bool = False,
-                 leaves_per_wave: int = 1):
+                 leaves_per_wave: int = 1, capture: bool = False):
         if opponent not in ("random", "greedy"):
             raise ValueError("opponent must be 'random' or 'greedy'")
         self.be = backend or default_backend()
@@ -33,6 +33,9 @@ class BatchedArena:
         # leaves_per_wave > 1: the MCTS player searches leaf-parallel with virtual loss (performance mode: K times larger
         # net batches for the few games of an Arena; its moves then differ from the reference's sequential search)
         self.leaves_per_wave = int(leaves_per_wave)
+        # capture (CUDA): the MCTS player's (net, wave) step is replayed from a CUDA graph (BatchedMCTS.search_captured) --
+        # same moves, one launch per step; ``evaluate`` must then be capturable (device tensors only, no host sync)
+        self.capture = bool(capture) and self.be.is_cuda
 
     def _opponent_actions(self, states, ply):
         if self.opponent == "random":
@@ -86,7 +89,7 @@ class BatchedArena:
                     started = True
                 else:
                     mcts.set_roots(roots)
-                mcts.search(self.evaluate, pack=True)                            # the net sees only the games RED moves in
+                mcts.search(self.evaluate, pack=True, capture=self.capture)      # the net sees only the games RED moves in
                 acts_red = mcts.sample_actions(0)                                # temp = 0: arg-max, ties uniformly
             else:
                 acts_red = torch.full((num,), -1, dtype=torch.int32, device=self.be.device)

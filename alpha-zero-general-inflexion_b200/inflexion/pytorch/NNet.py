@@ -37,6 +37,7 @@ class NNetWrapper(NeuralNet):
         self.nnet.to(self.device)
         self.infer_dtype = infer_dtype
         self._folded = None            # FoldedInference, rebuilt after every weight change
+        self.weights_version = 0       # bumped with it: owners of CUDA graphs that captured the folded net re-capture
 
     # ---- training (NNet.py:36-76) -----------------------------------------------------------------
     def train(self, examples, verbose=True):
@@ -151,7 +152,7 @@ class NNetWrapper(NeuralNet):
             for name, mod in swapped.items():              # plain BatchNorm modules back (they share the trained tensors)
                 setattr(self.nnet, name, mod)
             del model
-        self._folded = None
+        self.weights_changed()
         return history
 
     # ---- inference --------------------------------------------------------------------------------
@@ -184,6 +185,7 @@ class NNetWrapper(NeuralNet):
 
     def weights_changed(self):
         self._folded = None
+        self.weights_version += 1
 
     # ---- losses (NNet.py:96-100) --------------------------------------------------------------------
     def loss_pi(self, targets, outputs):
@@ -203,4 +205,4 @@ class NNetWrapper(NeuralNet):
             raise FileNotFoundError(f"No model in path {filepath}")
         checkpoint = torch.load(filepath, map_location=self.device)
         self.nnet.load_state_dict(checkpoint["state_dict"])
-        self._folded = None
+        self.weights_changed()

@@ -152,9 +152,12 @@ class BatchedMCTS:
         """args.numMCTSSims / args.cpuct for the searches that follow.  A CUDA graph captured earlier has the old values
         baked into its kernel arguments: ``params_version`` changes so that owners of such graphs (SelfPlayEngine)
         re-capture."""
+        cp = float(np.float32(cpuct))
+        if int(num_sims) == self.num_sims and cp == self.cfg.cpuct:
+            return                                             # unchanged: captured graphs stay valid
         self.params_version = getattr(self, "params_version", 0) + 1
-        self.num_sims = int(num_sims)
-        self.be.check(self.be.dll.ifx_mcts_set_params(self._h, self.num_sims, float(np.float32(cpuct))))
+        self.num_sims, self.cfg.cpuct = int(num_sims), cp
+        self.be.check(self.be.dll.ifx_mcts_set_params(self._h, self.num_sims, cp))
 
     # ---- search ---------------------------------------------------------------------------------
     def wave(self, part: tuple[int, int] | None = None) -> None:
@@ -247,9 +250,14 @@ class BatchedMCTS:
                 self.nn_v.copy_(v.reshape(-1))
         self.evals_run += 1
 
-    def search(self, evaluate, pack: bool = False) -> None:
+    def search(self, evaluate, pack: bool = False, capture: bool = False, version=0) -> None:
         """All ``num_sims`` simulations of every game: num_sims x (wave, net) + a closing wave.  No host sync, unless
-        ``pack``: then ``plan_rows`` first (one sync) so the net only sees the games that search in this move."""
+        ``pack``: then ``plan_rows`` first (one sync) so the net only sees the games that search in this move.
+        ``capture`` (CUDA only): replay the (net, wave) step from a CUDA graph -- see ``search_captured``."""
+        if capture and self.be.is_cuda:
+            if pack and not self._adaptive:
+                self.plan_rows()
+            return self.search_captured(evaluate, version)
         if self._adaptive:
             return self.search_adaptive(evaluate)
         if pack:
@@ -281,6 +289,69 @@ class BatchedMCTS:
                     self.feed(evaluate)
             self.wave()
             st = self.status()
+
+    # ---- captured step ---------------------------------------------------------------------------
+    def _captured_step(self, evaluate, version):
+        """CUDA graph of ONE search step -- net forward on the pending leaves, then the tree wave that consumes the
+        answers -- captured on first use per net batch size, and again whenever ``version`` (the caller's token for the
+        net's weights) or the search parameters change.  The kernel arguments baked into it are the persistent
+        buffers of this object."""
+        if not self.be.is_cuda:
+            raise RuntimeError("search_captured needs the CUDA backend")
+        key = (version, getattr(self, "params_version", 0))
+        if getattr(self, "_steps_key", None) != key:
+            self._steps, self._steps_key = {}, key             # (drops the old graphs and their memory pools)
+        if self.rows_active in self._steps:
+            return self._steps[self.rows_active]
+        dev = self.be.device
+        rows = self.rows_active if self.rows_active < self.n_games else self.nn_in.shape[0]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                          # warm the allocator / cuDNN heuristics for this batch shape
+            x = self._packed_buffers(rows)["in"] if rows < self.n_games else self.nn_in
+            for _ in range(2):
+                if self.fused_head:
+                    evaluate(x, torch.empty((rows, 344), dtype=torch.float16, device=dev))
+                else:
+                    evaluate(x)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        counters = (self.waves_run, self.evals_run, self.rows_evaluated)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.feed(evaluate)
+            self.wave()
+        self.waves_run, self.evals_run, self.rows_evaluated = counters      # (capturing launches nothing)
+        self._steps[self.rows_active] = graph
+        return graph
+
+    def search_captured(self, evaluate, version=0) -> None:
+        """``search`` with every (net, wave) step replayed from one CUDA graph: the same kernels on the same data in the
+        same order, so the same result bit for bit, at one launch per simulation step instead of a dozen -- for the
+        object-per-game drop-in and small sets of games, where the eager loop is bound by launch latency.  Sequential
+        mode needs no read-back at all: ``num_sims`` steps complete every game (a wave on a finished game does
+        nothing).  Leaf-parallel mode looks at the device after every ceil(remaining / K) steps.  ``evaluate`` must be
+        capturable (device tensors in and out, no host sync) and must not change while ``version`` stays the same."""
+        step = self._captured_step(evaluate, version)
+
+        def replay(n):
+            for _ in range(n):
+                step.replay()
+            self.waves_run += n
+            self.evals_run += n
+            self.rows_evaluated += n * self.rows_active
+
+        self.wave()
+        if not self._adaptive:
+            replay(self.waves_per_search - 1)
+            return
+        while True:
+            st = self.status()
+            done = (st[:, 0] >= self.num_sims) | (st[:, 2] != 0)
+            if bool(done.all()):
+                return
+            remaining = int((self.num_sims - st[:, 0])[~done].max())
+            replay(max(1, -(-remaining // self.leaves_per_wave)))
 
     def wave_timing(self, enable: bool) -> None:
         """Bracket every (un-captured) wave launch with CUDA events inside the library call (see ifx_mcts_wave_timing)."""

@@ -38,7 +38,8 @@ class SelfPlayEngine:
         latency-bound wave fills issue slots the tensor-bound convolutions leave idle); results are identical -- games
         are independent.  Used with CUDA graphs and a dense batch only.  ``leaves_per_wave`` = K > 1: the leaf-parallel
         performance mode (virtual loss; BatchedMCTS) -- for small sets of games, where the sequential search leaves the
-        net with tiny batches; eager waves, not the reference's visit counts."""
+        net with tiny batches; one captured (net, wave) step replayed until the device reports the move done; not the
+        reference's visit counts."""
         self.be = backend or default_backend()
         self.G, self.num_sims, self.temp_threshold = int(n_games), int(num_sims), int(temp_threshold)
         self.max_turns, self.game_id_base = int(max_turns), int(game_id_base)
@@ -58,7 +59,11 @@ class SelfPlayEngine:
             self.ex_after = self.be.empty((self.max_moves, self.G, 64), torch.uint8)   # root after the move (its outcome)
             self.ex_counts = self.be.empty((self.max_moves, self.G, 343), torch.int32)
             self.ex_actions = self.be.empty((self.max_moves, self.G), torch.int32)
-        self.use_graph = (self.be.is_cuda if use_graph is None else bool(use_graph)) and not self.leaf_parallel
+        want_graph = self.be.is_cuda if use_graph is None else bool(use_graph)
+        self.use_graph = want_graph and not self.leaf_parallel
+        # leaf-parallel mode: the number of waves of a move is decided on the device, so the captured unit is one
+        # (net, wave) step (BatchedMCTS.search_captured) instead of the whole move
+        self.capture_step = want_graph and self.leaf_parallel and self.be.is_cuda
         self._graphs = {}                                         # net batch size -> captured search of one move
         # fixed sets of episodes (no auto_restart) thin out as games end: the net then runs on the live games only
         # (BatchedMCTS.plan_rows: one host read per move, a captured graph per batch size)
@@ -130,7 +135,7 @@ class SelfPlayEngine:
         CUDA graph (so the library can bracket it with events, see BatchedMCTS.wave_timing); a callable wraps each
         launch instead."""
         if self.leaf_parallel:                                   # waves until the device reports every game done
-            self.mcts.search(self.evaluate)
+            self.mcts.search(self.evaluate, capture=self.capture_step)
             self.my_launches += self.mcts.waves_per_search
             return
         if wave_timer is True:

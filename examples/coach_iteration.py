@@ -112,7 +112,7 @@ def main():
     for opp in ("random", "greedy"):
         t2 = time.time()
         one, two, dr = BatchedArena(nnet.predict_head, a.sims, opponent=opp, seed=2, max_turns=a.max_turns,
-                                    fused_head=True).playGames(a.arena)
+                                    fused_head=True, capture=True).playGames(a.arena)
         if rank == 0:
             print(f"arena vs {opp}: MCTS {one} / {opp} {two} / draws {dr}  ({a.arena} games in {time.time() - t2:.1f}s)", flush=True)
     if world > 1:

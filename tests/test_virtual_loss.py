@@ -6,6 +6,7 @@ every PUCT search must keep (Ns = sum of edge counts in every node, the root's v
 valid moves, determinism), (iii) closeness of the root visit distribution to the sequential search's, and (iv) what it
 is for: far fewer, larger net calls."""
 import numpy as np
+import pytest
 import torch
 
 from inflexion_b200.mcts_batched import BatchedMCTS
@@ -140,3 +141,37 @@ def test_selfplay_engine_leaf_parallel_emits_examples(backend):
     planes, pi, v = eng.examples()
     assert moves == 7 and planes.shape == (3 * 7 * 36, 4, 7, 7) and np.allclose(pi.sum(axis=1), 1.0)
     assert set(np.round(np.abs(v), 4).tolist()) <= {1.0, 0.0001}
+
+
+@pytest.mark.parametrize("K", [1, 4])
+def test_captured_search_control_flow(K):
+    """search_captured replays (net, wave) steps without looking at the device where it need not: with the graph
+    replaced by its eager body (no CUDA here) it must leave the same trees as search / search_adaptive."""
+    from hostsim import hostsim_backend
+    be = hostsim_backend()
+    G, sims = 5, 23
+    out = []
+    for captured in (False, True):
+        m = BatchedMCTS(G, sims, 1.0, seed=9, backend=be, leaves_per_wave=K)
+        m.reset(start_states(G, 12))
+        ev = lambda x: stub_policy_value(x)  # noqa: E731
+        if captured:
+            class Step:
+                def replay(self_inner):
+                    m.feed(ev)
+                    m.wave()
+            m._captured_step = lambda evaluate, version: Step()
+        stats = []
+        for mv in range(4):
+            if captured:
+                m.search_captured(ev)
+            else:
+                m.search(ev)
+            m.raise_on_faults()
+            st = m.root_stats(want_q=True)
+            stats.append((st["counts"].clone(), st["q32"].clone()))
+            m.advance(m.sample_actions(0))
+        out.append(stats)
+    for (c0, q0), (c1, q1) in zip(*out):
+        assert torch.equal(c0, c1) and torch.equal(q0.view(torch.int32), q1.view(torch.int32))
+        assert int(c0.sum(1).min()) >= sims - 1

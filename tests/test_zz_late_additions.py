@@ -112,3 +112,76 @@ def test_example_set_equals_the_expanded_examples(backend, fix_alignment):
     all_planes = np.concatenate([planes, ps]).astype(np.float32)
     all_v = np.concatenate([v, vs]).astype(np.float32)
     assert np.array_equal(pu.cpu().numpy(), all_planes[idx]) and np.array_equal(vu.cpu().numpy(), all_v[idx])
+
+
+# ---- captured (net, wave) step: BatchedMCTS.search_captured and its users ------------------------------------------------
+def _net_on_gpu(be):
+    from inflexion_b200.inflexion.InflexionGame import InflexionGame
+    from inflexion_b200.inflexion.pytorch.NNet import NNetWrapper
+    torch.manual_seed(5)
+    game = InflexionGame(7, max_turns=343, max_power=6)
+    return game, NNetWrapper(game, device=be.device)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [1, 4])
+def test_object_api_captured_search_equals_eager(cuda_backend, K):
+    """MCTS.getActionProb with the device net: the graph-replayed search gives the eager search's visit counts and Q
+    values bit for bit, also after the weights change (the graph is captured again, not replayed stale)."""
+    from inflexion_b200.MCTS import MCTS
+    from inflexion_b200.utils import dotdict
+    game0, nnet = _net_on_gpu(cuda_backend)
+    runs = []
+    for captured in (True, False):
+        torch.manual_seed(5)
+        args = dotdict({"numMCTSSims": 30, "cpuct": 1.0, "captureSearch": captured, "leavesPerWave": K})
+        mcts, game, seen = MCTS(nnet, args, seed=11, backend=cuda_backend), game0.restarted(), []
+        for mv in range(5):
+            if mv == 3:                                   # new weights between two searches of the same object
+                with torch.no_grad():
+                    nnet.nnet.fc4.bias.add_(0.25)
+                    nnet.nnet.fc3.bias[:40].add_(0.5)
+                nnet.weights_changed()
+            pi = mcts.getActionProb(game, temp=1)
+            d = mcts.dump()
+            seen.append((pi.copy(), d["counts"].copy(), d["q32"].copy().view(np.int32)))
+            game = game.to_next_state(int(np.argmax(pi)))
+        with torch.no_grad():                             # undo, so that the second run sees the same sequence of nets
+            nnet.nnet.fc4.bias.sub_(0.25)
+            nnet.nnet.fc3.bias[:40].sub_(0.5)
+        nnet.weights_changed()
+        assert bool(getattr(mcts._tree, "_steps", None)) == captured      # (the graph path really ran / really did not)
+        runs.append(seen)
+    for (p0, c0, q0), (p1, c1, q1) in zip(*runs):
+        assert np.array_equal(c0, c1) and np.array_equal(q0, q1) and np.array_equal(p0, p1)
+        assert c0.sum() >= 29
+
+
+@pytest.mark.gpu
+def test_batched_arena_captured_equals_eager(cuda_backend):
+    """BatchedArena(capture=True) plays the same games as the eager loop (sequential and leaf-parallel search)."""
+    from inflexion_b200.arena_batched import BatchedArena
+    for K in (1, 4):
+        got = []
+        for capture in (False, True):
+            arena = BatchedArena(lambda x: stub_policy_value(x), 10, opponent="greedy", seed=4, max_turns=12,
+                                 backend=cuda_backend, record=True, leaves_per_wave=K, capture=capture)
+            got.append((arena.playGames(70, shard=False), arena.last_actions.copy(), arena.last_results.copy()))
+        assert got[0][0] == got[1][0] and sum(got[0][0]) == 70
+        assert np.array_equal(got[0][1], got[1][1]) and np.array_equal(got[0][2], got[1][2])
+
+
+@pytest.mark.gpu
+def test_selfplay_engine_leaf_parallel_captured_equals_eager(cuda_backend):
+    """SelfPlayEngine(leaves_per_wave=K): the captured step gives the eager waves' records."""
+    recs = []
+    for use_graph in (False, True):
+        eng = SelfPlayEngine(8, 24, lambda x: stub_policy_value(x), temp_threshold=3, seed=5, max_turns=9,
+                             backend=cuda_backend, leaves_per_wave=4, use_graph=use_graph)
+        assert eng.capture_step == use_graph
+        eng.play_episode()
+        eng.mcts.raise_on_faults()
+        recs.append(eng.records())
+    for k in recs[0]:
+        a, b = recs[0][k], recs[1][k]
+        assert (torch.equal(a, b) if torch.is_tensor(a) else np.array_equal(a, b)), k
