@@ -301,6 +301,9 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+LARGE_LAUNCH_GAMES, LARGE_LAUNCH_NODES = 16384, 640
+
+
 def ncu_traffic(kernel: str, workload: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
     of this same command (profiles/traffic.json, written by tools/summarize_profiles.py); None if not captured."""
@@ -471,21 +474,37 @@ def run_ours(a):
     if world == 1 and a.net == "default" and not a.no_extra_rooflines:
         del eng
         torch.cuda.empty_cache()
-        try:
-            stub = SelfPlayEngine(a.games, a.sims, None, cpuct=1.0, temp_threshold=30, seed=2023, max_turns=343, record=False,
-                                  backend=be, fused_head=False, nodes_per_game=a.nodes, auto_restart=True)
-            stub.evaluate = stub_kernel_evaluator(stub.mcts)
-            for _ in range(3):
-                stub.play_move()
-            r = tree_roofline(stub, max(3, min(a.steps, 8)), hbm_peak, peak_src, ncu_traffic("tree_wave_kernel", "stub") if (a.games, a.sims) == (4096, 100) else None)
-            for k in ("_instr_ms", "_tree_ms", "_expansions"):
-                r.pop(k)
-            r["workload"] = "same games x sims with the deterministic stub evaluator (tree + rules only, deeper trees)"
-            extra["roofline_tree_stub"] = r
-            del stub
-            torch.cuda.empty_cache()
-        except Exception as e:                              # noqa: BLE001
-            extra["roofline_tree_stub"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+        def stub_tree(games, nodes, traffic, workload):
+            """tree_roofline of a fresh engine with the deterministic stub evaluator (one kernel of the library)."""
+            try:
+                stub = SelfPlayEngine(games, a.sims, None, cpuct=1.0, temp_threshold=30, seed=2023, max_turns=343, record=False,
+                                      backend=be, fused_head=False, nodes_per_game=nodes, auto_restart=True)
+                stub.evaluate = stub_kernel_evaluator(stub.mcts)
+                for _ in range(3):
+                    stub.play_move()
+                r = tree_roofline(stub, max(3, min(a.steps, 8)), hbm_peak, peak_src, traffic)
+                stub.mcts.raise_on_faults()
+                for k in ("_instr_ms", "_tree_ms", "_expansions"):
+                    r.pop(k)
+                r["workload"], r["games_per_launch"] = workload, games
+                del stub
+                return r
+            except Exception as e:                          # noqa: BLE001
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
+            finally:
+                torch.cuda.empty_cache()
+        extra["roofline_tree_stub"] = stub_tree(
+            a.games, a.nodes, ncu_traffic("tree_wave_kernel", "stub") if (a.games, a.sims) == (4096, 100) else None,
+            "same games x sims with the deterministic stub evaluator (tree + rules only, deeper trees)")
+        # One warp per game and 4 096 warps fit on the 148 SMs at once, so a 4 096-game launch lasts as long as its DEEPEST
+        # descent (profiles/r2_trace_stub.txt: mean warp lifetime 10.7 us, longest 16.9 us).  With more games per launch than
+        # resident warps the CTAs that finish early make room for the rest and the tail is amortised: the same kernel,
+        # 4x the games (node pool of 640 slots per game so that it fits beside nothing else: 74 GB).
+        if (a.games, a.sims) == (4096, 100):
+            extra["roofline_tree_stub_16k"] = stub_tree(
+                LARGE_LAUNCH_GAMES, LARGE_LAUNCH_NODES, ncu_traffic("tree_wave_kernel", "stub16k"),
+                f"{LARGE_LAUNCH_GAMES} games per launch (4x the headline's; more warps than the SMs hold at once), stub evaluator")
         try:
             extra["roofline_rules"] = rules_roofline(be, a.states, max(a.steps, 10), hbm_peak, peak_src)
         except Exception as e:                              # noqa: BLE001

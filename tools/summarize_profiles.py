@@ -72,8 +72,13 @@ full_summary(os.path.join(g, f"tree_stub_{tag}.ncu-rep"), os.path.join(OUT, f"{t
              "tree_wave_kernel inside bench.py --net stub (tree + rules only, 4096 games x 100 sims/move)")
 full_summary(os.path.join(g, f"rules_{tag}.ncu-rep"), os.path.join(OUT, f"{tag}_ncu_rules_mask_step_kernel.txt"),
              "rules_mask_step_kernel, bench.py --workload rules (4 Mi states per launch)")
+big = os.path.join(g, f"tree_stub16k_{tag}.ncu-rep")
+if os.path.exists(big):
+    full_summary(big, os.path.join(OUT, f"{tag}_ncu_tree_wave_kernel_stub16k.txt"),
+                 "tree_wave_kernel inside bench.py --net stub --games 16384 --nodes 640 (4x the headline's games per launch)")
 traffic = {"tree_wave_kernel": {"default": traffic_of(os.path.join(g, f"tree_default_{tag}.ncu-rep")),
-                                "stub": traffic_of(os.path.join(g, f"tree_stub_{tag}.ncu-rep"))},
+                                "stub": traffic_of(os.path.join(g, f"tree_stub_{tag}.ncu-rep")),
+                                **({"stub16k": traffic_of(big)} if os.path.exists(big) else {})},
            "rules_mask_step_kernel": {"rules": traffic_of(os.path.join(g, f"rules_{tag}.ncu-rep"))}}
 json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
