@@ -5,9 +5,9 @@
 
 One object owns one device tree (a ``BatchedMCTS`` with a single game); ``getActionProb`` runs the
 ``numMCTSSims`` simulations as kernel waves, keeps the tables between calls exactly as the reference does
-(Coach.py:110 builds one MCTS per episode) and reads the root visit counts back.  The net is called through
-``nnet.predict_batch`` (device tensors) when it has one, else through the reference-style
-``nnet.predict(planes)`` once per leaf.
+(Coach.py:110 builds one MCTS per episode) and reads the root visit counts back.  A device net is called through
+``nnet.predict_head`` (raw float16 head rows; softmax / tanh in the tree kernel) or ``nnet.predict_batch``, any other
+net through the reference-style ``nnet.predict(planes)`` once per leaf.
 
 Random draws (leaf symmetry, MCTS.py:92; arg-max tie break, MCTS.py:53) come from the device's counter-based
 Philox stream, keyed by a seed taken from numpy's global RNG at construction -- so ``np.random.seed`` still
@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from .Game import Game
+from .backend import default_backend
 from .mcts_batched import BatchedMCTS
 
 EPS = 1e-8
@@ -46,7 +47,9 @@ class MCTS:
         self._last_turn = -1
 
     # ---- net adapter ----------------------------------------------------------------------------------
-    def _evaluate(self, nn_in: torch.Tensor):
+    def _evaluate(self, nn_in: torch.Tensor, out: torch.Tensor | None = None):
+        if out is not None:                                               # fused head: raw binary16 rows for the tree kernel
+            return self.nnet.predict_head(nn_in, out)
         if hasattr(self.nnet, "predict_batch") and getattr(self.nnet, "device", nn_in.device) == nn_in.device:
             return self.nnet.predict_batch(nn_in)
         pis, vs = [], []
@@ -64,7 +67,7 @@ class MCTS:
         t, n = self._tree, self.nnet
         if (t.be.is_cuda and dict(self.args).get("captureSearch", True) and hasattr(n, "predict_batch")
                 and hasattr(n, "weights_version") and getattr(n, "device", None) == t.be.device):
-            t.search_captured(n.predict_batch, version=(id(n), n.weights_version))
+            t.search_captured(n.predict_head if t.fused_head else n.predict_batch, version=(id(n), n.weights_version))
         else:
             t.search_adaptive(self._evaluate)
         t.raise_on_faults()
@@ -74,7 +77,13 @@ class MCTS:
         state = game._state.copy()
         state["tag"] = self._game_id
         if self._tree is None:
-            self._tree = BatchedMCTS(1, sims, cpuct, seed=self._seed, backend=self._backend,
+            # a float16 device net on the tree's GPU hands its raw head output (343 logits + value pre-activation) to the
+            # tree kernel, which applies softmax / tanh itself -- as the batched self-play does (Coach._evaluator): six
+            # small launches fewer per simulation.  args.fusedHead = False keeps predict_batch's float32 (pi, v).
+            be, n = self._backend or default_backend(), self.nnet
+            fused = bool(be.is_cuda and dict(self.args).get("fusedHead", True) and hasattr(n, "predict_head")
+                         and getattr(n, "device", None) == be.device and getattr(n, "infer_dtype", None) == torch.float16)
+            self._tree = BatchedMCTS(1, sims, cpuct, seed=self._seed, backend=be, fused_head=fused,
                                      nodes_per_game=min(16383, max(4096, 16 * sims)),
                                      terminal_sims_per_wave=0,   # one game: fewest launches, no tail to bound
                                      # args.leavesPerWave (not in the reference; default 1 = its sequential search): K > 1

@@ -124,8 +124,8 @@ def _net_on_gpu(be):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("K", [1, 4])
-def test_object_api_captured_search_equals_eager(cuda_backend, K):
+@pytest.mark.parametrize("K,fused", [(1, True), (4, True), (1, False)])
+def test_object_api_captured_search_equals_eager(cuda_backend, K, fused):
     """MCTS.getActionProb with the device net: the graph-replayed search gives the eager search's visit counts and Q
     values bit for bit, also after the weights change (the graph is captured again, not replayed stale)."""
     from inflexion_b200.MCTS import MCTS
@@ -134,7 +134,7 @@ def test_object_api_captured_search_equals_eager(cuda_backend, K):
     runs = []
     for captured in (True, False):
         torch.manual_seed(5)
-        args = dotdict({"numMCTSSims": 30, "cpuct": 1.0, "captureSearch": captured, "leavesPerWave": K})
+        args = dotdict({"numMCTSSims": 30, "cpuct": 1.0, "captureSearch": captured, "leavesPerWave": K, "fusedHead": fused})
         mcts, game, seen = MCTS(nnet, args, seed=11, backend=cuda_backend), game0.restarted(), []
         for mv in range(5):
             if mv == 3:                                   # new weights between two searches of the same object
@@ -151,6 +151,7 @@ def test_object_api_captured_search_equals_eager(cuda_backend, K):
             nnet.nnet.fc3.bias[:40].sub_(0.5)
         nnet.weights_changed()
         assert bool(getattr(mcts._tree, "_steps", None)) == captured      # (the graph path really ran / really did not)
+        assert mcts._tree.fused_head == fused                             # (raw fp16 head rows / predict_batch's (pi, v))
         runs.append(seen)
     for (p0, c0, q0), (p1, c1, q1) in zip(*runs):
         assert np.array_equal(c0, c1) and np.array_equal(q0, q1) and np.array_equal(p0, p1)
