@@ -186,3 +186,35 @@ def test_selfplay_engine_leaf_parallel_captured_equals_eager(cuda_backend):
     for k in recs[0]:
         a, b = recs[0][k], recs[1][k]
         assert (torch.equal(a, b) if torch.is_tensor(a) else np.array_equal(a, b)), k
+
+
+@pytest.mark.parametrize("cpuct", [0.0, 0.05, 4.0, 37.5])
+def test_extreme_cpuct_and_tiny_simulation_counts(backend, cpuct):
+    """PUCT at the edges of its parameter range: cpuct = 0 (u = Q alone: every unvisited edge ties at 0 and the first
+    valid action wins, MCTS.py:118-128), a tiny and a huge exploration constant, 2 / 3 / 17 simulations per move (one
+    simulation only expands the root: the reference then divides 0 by 0, MCTS.py:58-59), short games that end inside
+    the search.  Visit counts and sampled actions against the oracle."""
+    from oracle.inflexion_mcts import self_play_moves
+    for sims in (2, 3, 17):
+        for mode in ("float", "dyadic"):
+            G, seed, moves = 3, 5, 5
+            max_turns = np.array([343, 5, 8])
+            m = BatchedMCTS(G, sims, cpuct, seed=seed, backend=backend)
+            m.reset(start_states(G, max_turns, tags=np.arange(G) + 7))
+            orc = [self_play_moves(stub_predict(mode), sims, cpuct, PhiloxDraws(seed, game=7 + i), temp_threshold=2,
+                                   max_moves=moves, max_turns=int(max_turns[i])) for i in range(G)]
+            alive = [True] * G
+            for mv in range(moves):
+                m.search(stub_eval(mode))
+                m.raise_on_faults()
+                counts = m.root_stats()["counts"].cpu().numpy()
+                acts = m.sample_actions(2)
+                a = acts.cpu().numpy()
+                for i in range(G):
+                    if not alive[i]:
+                        continue
+                    rec = next(orc[i])
+                    assert np.array_equal(counts[i], rec["counts"]) and a[i] == rec["action"], (cpuct, sims, mode, mv, i)
+                    if rec["game"].outcome != 0:
+                        alive[i] = False
+                m.advance(acts)
