@@ -218,3 +218,37 @@ def test_extreme_cpuct_and_tiny_simulation_counts(backend, cpuct):
                     if rec["game"].outcome != 0:
                         alive[i] = False
                 m.advance(acts)
+
+
+def test_rules_on_arbitrary_boards(backend):
+    """Move masks and transitions on boards that need not be reachable: random density up to a full board, random
+    powers 1..6 for both colours (total power up to ~200, far beyond the spawn limit), turns up to the last one.
+    Against the oracle, bit for bit (InflexionGame.py:93-100, 273-310)."""
+    import oracle.inflexion_rules as R
+    from inflexion_b200 import rules
+    from inflexion_b200.state import STATE_DTYPE, players_of, unpack_boards, unpack_masks
+    rng = np.random.default_rng(123)
+    n = 6000
+    occ = rng.random((n, 49)) < rng.random(n)[:, None]
+    sign = np.where(rng.random((n, 49)) < rng.random(n)[:, None], 1, -1)
+    b = (occ * sign * rng.integers(1, 7, size=(n, 49))).astype(np.int64)
+    p = np.where(rng.random(n) < 0.5, 1, -1)
+    t = rng.integers(0, 343, size=n)
+    t[::7], t[1::7] = 342, 341
+    valid = R.batch_valid_mask(b, p)
+    has = valid.reshape(n, -1).sum(1) > 0
+    assert 0.9 * n < has.sum() < n                                     # (a side without stacks on a full board cannot move)
+    st_all = backend.states_tensor(pack_states(b, p, t))
+    masks_all, _, _ = rules.mask_step(st_all, None, backend=backend)
+    assert np.array_equal(unpack_masks(masks_all.cpu().numpy()), valid)
+    b, p, t, valid = b[has], p[has], t[has], valid[has]
+    a = np.array([rng.choice(np.flatnonzero(f)) for f in valid.reshape(len(b), -1)])
+    masks, nxt, status = rules.mask_step(backend.states_tensor(pack_states(b, p, t)),
+                                         torch.from_numpy(a.astype(np.int32)).to(backend.device), backend=backend)
+    assert int(status.abs().sum()) == 0
+    nb, npl, nt, out = R.batch_step(b, p, t, a)
+    got = nxt.cpu().numpy().view(STATE_DTYPE).reshape(-1)
+    assert np.array_equal(unpack_boards(got), nb) and np.array_equal(got["outcome"], out)
+    assert np.array_equal(got["turn"], nt) and np.array_equal(players_of(got), npl)
+    assert np.array_equal(got["total_power"], np.abs(nb).sum(axis=1))
+    assert np.abs(b).sum(1).max() > 150 and (out != 0).any()
