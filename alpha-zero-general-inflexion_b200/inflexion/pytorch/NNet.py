@@ -75,7 +75,11 @@ class NNetWrapper(NeuralNet):
             # (NNet.py:52,58); the original modules (sharing the same tensors) are put back at the end.
             from torch.nn.parallel import DistributedDataParallel as DDP
             swapped = {}
-            if self.device.type == "cuda":
+            # ``args.dp_sync_bn = False`` (optional): every rank normalises with the statistics of its OWN 512/world rows --
+            # no collective inside the layers (SyncBatchNorm costs 12 small all-gathers / all-reduces per step, about as
+            # much as the rest of a latency-bound step at 8 GPUs), at the price of leaving the reference's semantics;
+            # the running statistics are then averaged over the ranks at the end of train().
+            if self.device.type == "cuda" and args.get("dp_sync_bn", True):
                 for name, mod in list(self.nnet.named_children()):
                     if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
                         swapped[name] = mod

@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--arena", type=int, default=20)
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--gather", action="store_true", help="all-gather the un-expanded self-play records (final example gather)")
+    ap.add_argument("--local-bn", action="store_true",
+                    help="data-parallel training with per-rank BatchNorm statistics (NNet args.dp_sync_bn = False)")
     ap.add_argument("--compact", action="store_true",
                     help="keep un-expanded records and expand examples per training batch (selfplay.ExampleSet): thousands of games")
     a = ap.parse_args()
@@ -43,6 +45,8 @@ def main():
     torch.manual_seed(0)                                        # identical initial weights on every rank
     game = InflexionGame(7, max_turns=a.max_turns, max_power=6)
     nnet_mod.args["epochs"] = a.epochs
+    if a.local_bn:
+        nnet_mod.args["dp_sync_bn"] = False
     nnet = nnet_mod.NNetWrapper(game)
     coach = Coach(game, nnet, dotdict({"numMCTSSims": a.sims, "cpuct": 1, "tempThreshold": 30, "numEps": a.games * world}))
 
@@ -74,7 +78,7 @@ def main():
     steps = a.epochs * int(sum(int(x) for x in n_all) / nnet_mod.args.batch_size)
     if rank == 0:
         print(f"examples per rank: {[int(x) for x in n_all]} (games end at different moves, so the counts may differ)", flush=True)
-        print("train: %d steps in %.1fs (%.2f ms/step, global batch %d = %d per rank); loss_pi %.3f -> %.3f, loss_v %.3f -> %.3f; "
+        print("train" + (" (per-rank BatchNorm statistics)" if a.local_bn else "") + ": %d steps in %.1fs (%.2f ms/step, global batch %d = %d per rank); loss_pi %.3f -> %.3f, loss_v %.3f -> %.3f; "
               "parameters and BatchNorm buffers identical on all ranks"
               % (steps, t_tr, 1e3 * t_tr / max(steps, 1), nnet_mod.args.batch_size, nnet_mod.args.batch_size // world,
                  hist[0][0], hist[-1][0], hist[0][1], hist[-1][1]), flush=True)
