@@ -62,3 +62,47 @@ def test_header_is_plain_c_and_the_c_example_compiles(tmp_path):
            os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", str(out), "-ldl"]
     subprocess.run(cmd, check=True, capture_output=True)
     assert out.exists()
+
+
+def test_argument_errors_are_reported_not_crashed():
+    """Every entry point checks its arguments before touching memory: null pointers with n > 0, negative sizes, bad enums
+    and inconsistent search configurations come back as IFX_E_ARG (-1) -- through the CPU build of the same sources."""
+    import ctypes as C
+    import numpy as np
+    from hostsim import hostsim_backend
+    from inflexion_b200 import _capi
+    dll = hostsim_backend().dll
+    buf = np.zeros(4096, dtype=np.uint8)
+    p = buf.ctypes.data
+    E = _capi.IFX_E_ARG if hasattr(_capi, "IFX_E_ARG") else -1
+    assert dll.ifx_rules_mask_step(None, None, 5, None, None, None, None) == E
+    assert dll.ifx_rules_mask_step(p, None, -1, p, None, None, None) == E
+    assert dll.ifx_rules_mask_step_host(None, None, 3, None, None, None) == E
+    assert dll.ifx_rules_planes(None, None, 4, 0, None, None) == E
+    assert dll.ifx_rules_planes(p, None, 4, 7, p, None) == E                      # dtype code
+    assert dll.ifx_rules_symmetries(p, 1, 0, 4, p, None) == E                     # channels
+    assert dll.ifx_rules_symmetries(p, 1, 4, 3, p, None) == E                     # element size
+    assert dll.ifx_rules_transform(p, None, 1, 4, 4, p, None) == E                # no symmetry codes
+    assert dll.ifx_rules_random_actions(None, 3, 1, 0, None, None) == E
+    assert dll.ifx_rules_greedy_actions(None, 3, None, None) == E
+    base = dict(n_games=2, nodes_per_game=256, hash_per_game=512, max_depth=352, num_sims=10, cpuct=1.0, seed=1,
+                policy_is_logits=0, terminal_sims_per_wave=1, dirichlet_alpha=0.0, dirichlet_eps=0.0, leaves_per_wave=1)
+    cfg, lay = _capi.MctsConfig(**base), _capi.MctsLayout()
+    assert dll.ifx_mcts_get_layout(C.byref(cfg), C.byref(lay)) == 0 and dll.ifx_mcts_workspace_bytes(C.byref(cfg)) > 0
+    bad = ({"n_games": 0}, {"n_games": -3}, {"nodes_per_game": 0}, {"nodes_per_game": 16384}, {"hash_per_game": 100},
+           {"max_depth": 0}, {"max_depth": 10000}, {"num_sims": -1}, {"num_sims": 1 << 17}, {"leaves_per_wave": 17},
+           {"leaves_per_wave": -2}, {"dirichlet_eps": 2.0}, {"dirichlet_eps": 0.25, "dirichlet_alpha": 0.0},
+           {"leaves_per_wave": 4, "dirichlet_eps": 0.25, "dirichlet_alpha": 0.3})
+    for kw in bad:
+        cfg = _capi.MctsConfig(**{**base, **kw})
+        h = C.c_void_p()
+        assert dll.ifx_mcts_get_layout(C.byref(cfg), C.byref(lay)) == E, kw
+        assert dll.ifx_mcts_workspace_bytes(C.byref(cfg)) == 0, kw
+        assert dll.ifx_mcts_create(C.byref(cfg), p, 4096, C.byref(h)) == E and not h.value, kw
+    cfg, h = _capi.MctsConfig(**base), C.c_void_p()
+    assert dll.ifx_mcts_create(C.byref(cfg), p, 4096, C.byref(h)) == E            # workspace too small
+    assert dll.ifx_mcts_wave(None, None, 0, None, None, None) == E                # null handle
+    assert dll.ifx_mcts_status(None, None, None) == E
+    assert dll.ifx_mcts_set_params(None, 5, 1.0) == E
+    assert dll.ifx_mcts_root_stats(None, None, None, None, None, None, None) == E
+    dll.ifx_mcts_destroy(None)                                                    # a no-op
